@@ -1,0 +1,194 @@
+// xgb_stencil.cuh -- hand-written device templates for xgrid sweeps on sm_100a.
+//
+// The code generator (xgrid_b200/lang/cudagen.py) lowers one *sweep group* -- a
+// run of stencil statements that the reference executes as separate mask-
+// predicated full-grid loop nests (xgrid/lang/generator.py:285-364) -- to one
+// __global__ function assembled from the primitives below.  The generator only
+// emits the per-point expressions and the list of row windows they read; every
+// performance-relevant decision (thread->point mapping, vector width, window
+// loads, mask fetch, predicated stores, marching, shared-memory staging) lives
+// here.
+//
+// Memory model (DESIGN.md "Data layout in HBM"):
+//   * a time level is a C-order array padded with `ghost` zero rows on both
+//     sides of axis 0 plus a small linear slack, so a relative tap is a single
+//     signed linear offset and out-of-range taps never fault (the reference
+//     reads whatever is adjacent);
+//   * the boundary mask is uint8 per point; `flags` holds one byte per
+//     XGB_CHUNK consecutive points that is non-zero iff any mask byte in the
+//     chunk is non-zero, so interior threads never touch the mask.
+#pragma once
+
+typedef signed char int8_t;
+typedef short int16_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+
+#define XGB_CHUNK_SHIFT 7
+#define XGB_CHUNK (1 << XGB_CHUNK_SHIFT)
+#define XGB_DEV __device__ __forceinline__
+
+namespace xgb {
+
+// --------------------------------------------------------------------------- math
+// gcc folds pow(x, 2.0) to x*x at the reference's default -O2;
+// emitting the product keeps fp64 results bit-identical.
+template <class T> XGB_DEV T sq(T x) { return x * x; }
+
+// C semantics of the reference's int32 `/` and `%` are what CUDA C gives too.
+
+// --------------------------------------------------------------------------- vector access
+template <int BYTES> struct Pack;
+template <> struct Pack<1>  { typedef uint8_t  type; };
+template <> struct Pack<2>  { typedef uint16_t type; };
+template <> struct Pack<4>  { typedef uint32_t type; };
+template <> struct Pack<8>  { typedef uint2    type; };
+template <> struct Pack<16> { typedef uint4    type; };
+
+// load V consecutive elements starting at an address aligned to V*sizeof(T)
+template <class T, int V>
+XGB_DEV void ld_vec(const T *p, T (&out)[V]) {
+    constexpr int B = V * (int)sizeof(T);
+    if constexpr (B <= 16) {
+        typedef typename Pack<B>::type P;
+        union { P pk; T el[V]; } u;
+        u.pk = *reinterpret_cast<const P *>(p);
+#pragma unroll
+        for (int i = 0; i < V; ++i) out[i] = u.el[i];
+    } else {
+        static_assert(B % 16 == 0, "vector must be a multiple of 16 bytes");
+        constexpr int N = B / 16, E = 16 / (int)sizeof(T);
+        union { uint4 pk[N]; T el[V]; } u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) u.pk[i] = reinterpret_cast<const uint4 *>(p)[i];
+#pragma unroll
+        for (int i = 0; i < V; ++i) out[i] = u.el[i];
+        (void)E;
+    }
+}
+
+template <class T, int V>
+XGB_DEV void st_vec(T *p, const T (&v)[V]) {
+    constexpr int B = V * (int)sizeof(T);
+    if constexpr (B <= 16) {
+        typedef typename Pack<B>::type P;
+        union { P pk; T el[V]; } u;
+#pragma unroll
+        for (int i = 0; i < V; ++i) u.el[i] = v[i];
+        *reinterpret_cast<P *>(p) = u.pk;
+    } else {
+        constexpr int N = B / 16;
+        union { uint4 pk[N]; T el[V]; } u;
+#pragma unroll
+        for (int i = 0; i < V; ++i) u.el[i] = v[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) reinterpret_cast<uint4 *>(p)[i] = u.pk[i];
+    }
+}
+
+// Row window: w[k] = row[LO + k] for k in [0, V + HI - LO), where `row` points
+// at the thread's first point (aligned to V elements) shifted by the tap's
+// outer-axis offset.  The aligned body is one vector load; the LO/HI fringes
+// are scalar loads that hit L1 (they are a neighbouring thread's body).
+template <class T, int V, int LO, int HI>
+XGB_DEV void ld_window(const T *row, T (&w)[V + HI - LO]) {
+    static_assert(LO <= 0 && HI >= 0, "window must contain the centre");
+    if constexpr (V > 1) {
+        T body[V];
+        ld_vec<T, V>(row, body);
+#pragma unroll
+        for (int i = 0; i < V; ++i) w[i - LO] = body[i];
+    } else {
+        w[-LO] = row[0];
+    }
+#pragma unroll
+    for (int k = LO; k < 0; ++k) w[k - LO] = row[k];
+#pragma unroll
+    for (int k = 0; k < HI; ++k) w[V - LO + k] = row[V + k];
+}
+
+// Same window, with the +-1 fringes taken from the neighbouring lanes' bodies
+// (warp shuffle) instead of extra loads.  Requires a full, converged warp whose
+// lanes own consecutive V-element bodies of the same row; lanes 0 / 31 fall
+// back to one scalar load each.
+template <class T, int V, int LO, int HI>
+XGB_DEV void ld_window_shfl(const T *row, T (&w)[V + HI - LO]) {
+    static_assert(LO >= -1 && HI <= 1, "shuffle window supports +-1 fringes");
+    T body[V];
+    ld_vec<T, V>(row, body);
+#pragma unroll
+    for (int i = 0; i < V; ++i) w[i - LO] = body[i];
+    const int lane = threadIdx.x & 31;
+    if constexpr (LO == -1) {
+        T left = __shfl_up_sync(0xffffffffu, body[V - 1], 1);
+        if (lane == 0) left = row[-1];
+        w[0] = left;
+    }
+    if constexpr (HI == 1) {
+        T right = __shfl_down_sync(0xffffffffu, body[0], 1);
+        if (lane == 31) right = row[V];
+        w[V - LO] = right;
+    }
+}
+
+// Store v[i] where bit i of `written` is set (points whose mask matched no
+// statement keep the ring buffer's previous content).
+template <class T, int V>
+XGB_DEV void st_pred(T *p, const T (&v)[V], unsigned written) {
+    constexpr unsigned ALL = (V >= 32) ? 0xffffffffu : ((1u << V) - 1u);
+    if (written == ALL) {
+        st_vec<T, V>(p, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i)
+            if (written & (1u << i)) p[i] = v[i];
+    }
+}
+
+// --------------------------------------------------------------------------- mask
+// m[i] = boundary value of point base+i (0 when the chunk flag says "all zero").
+template <int V>
+XGB_DEV void ld_mask(const uint8_t *mask, const uint8_t *flags, int64_t base, int (&m)[V]) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = 0;
+    if (mask == nullptr) return;
+    if (flags != nullptr && flags[base >> XGB_CHUNK_SHIFT] == 0) return;
+    if constexpr (V == 1) {
+        m[0] = mask[base];
+    } else {
+        uint8_t b[V];
+        ld_vec<uint8_t, V>(mask + base, b);
+#pragma unroll
+        for (int i = 0; i < V; ++i) m[i] = b[i];
+    }
+}
+
+// --------------------------------------------------------------------------- geometry
+// Dense sweeps view an N-d grid as rows x cols (cols = contiguous axis).
+// blockDim = (TX, TY); a thread owns V consecutive columns of one row.
+struct Tile {
+    int64_t row;    // global row of this thread
+    int64_t col;    // first column of this thread
+    bool active;
+};
+
+template <int V>
+XGB_DEV Tile dense_tile(int64_t rows, int64_t cols) {
+    Tile t;
+    const int64_t rb = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+    t.row = rb * blockDim.y + threadIdx.y;
+    t.col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    t.active = (t.row < rows) && (t.col < cols);
+    return t;
+}
+
+// overstep="limit" / "wrap" (xgrid/lang/generator.py:172-177) with per-axis
+// extents paired correctly (the reference pairs them wrongly off-square, F1).
+XGB_DEV int64_t clamp_idx(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+XGB_DEV int64_t wrap_idx(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
+
+}  // namespace xgb

@@ -1,0 +1,304 @@
+"""``xgrid.Grid`` with device-resident time levels.
+
+Public surface and ring semantics follow the reference
+(xgrid/xgrid/__init__.py:21-86): ``Grid(shape, dtype)``, ``.now``, ``[]``,
+``.boundary`` (a mutable int32 NumPy array), ``.shape``, ``.dimension``,
+``fill``; ``_extend_time(depth)`` appends zero levels and truncates to
+``depth`` (:43-47); ``_op_invoke`` rotates the oldest buffer to the front
+(:52-54).  What changed is where the data lives:
+
+* every level is an HBM allocation laid out C-order with ``ghost`` zero rows
+  on both sides of axis 0 (these become the halo rows of a slab when the grid
+  is sharded) and a small linear slack, so a stencil tap is one signed linear
+  offset and never faults;
+* rotation swaps handles, never data;
+* the host sees data only through ``.now`` / ``[]`` / ``_data`` which copy
+  device -> host on demand and hand the level back to the host (the user may
+  write through the returned array); the next kernel call re-uploads it;
+* the int32 ``boundary`` array is compiled on upload into a uint8 device mask,
+  per-128-point "any non-zero" flags and compacted index lists per mask value.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from .log import Logger
+from .types import Boolean, Floating, Grid as GridT, Integer, Structure, Value, parse_annotation
+
+SLACK = 64          # elements of linear slack before / after the padded array
+CHUNK = 128         # points per mask flag (XGB_CHUNK in xgb_stencil.cuh)
+ALIGN = 256
+
+
+def parse_numpy_dtype(t: Value):
+    if isinstance(t, Structure):
+        return np.dtype([(n, parse_numpy_dtype(ft)) for n, ft in t.elements], align=True)
+    return np.dtype(t.np_dtype)
+
+
+class _Level:
+    """One time level: device allocation + optional host mirror."""
+    __slots__ = ("dev", "host", "where", "raw")
+
+    def __init__(self, host=None) -> None:
+        self.dev = 0            # device pointer of the first *real* element (0 = not allocated)
+        self.host = host        # np.ndarray or None (an all-zero level never touched by the host)
+        self.where = "host" if host is not None else "zero"
+        self.raw = 0            # base of the padded device allocation
+
+
+class Grid:
+    def __init__(self, shape, dtype) -> None:
+        self.logger = Logger(self)
+        elem = parse_annotation(dtype)
+        if not isinstance(elem, Value):
+            self.logger.dead(f"Grid element should be value instead of '{elem}'")
+        if isinstance(shape, int):
+            shape = (shape,)
+        self.element = elem
+        self.shape = tuple(int(s) for s in shape)
+        self.numpy_dtype = parse_numpy_dtype(elem)
+        self.typing = GridT(elem, len(self.shape))
+        self.size = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        self.itemsize = self.numpy_dtype.itemsize
+        self.stride0 = self.size // self.shape[0] if self.shape and self.shape[0] else 1
+
+        self._ring: list[_Level] = [_Level(np.zeros(self.shape, self.numpy_dtype))]
+        self._scratch: _Level | None = None
+        self._boundary = np.zeros(self.shape, dtype=np.int32)
+        self._mask_touched = True
+        self._mask_snapshot = None
+        self._mask_dev = 0
+        self._flags_dev = 0
+        self._mask_any = False
+        self._lists: dict = {}          # mask value -> (device ptr, count)
+        self._mask_version = 0
+        self._ghost = 1                 # zero rows on both sides of axis 0
+        self._allocs: list[int] = []    # raw device allocations to free
+        self._rt = None
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def dimension(self) -> int:
+        return len(self.shape)
+
+    @property
+    def boundary(self) -> np.ndarray:
+        self._mask_touched = True
+        return self._boundary
+
+    @boundary.setter
+    def boundary(self, value) -> None:
+        arr = np.asarray(value, dtype=np.int32)
+        if arr.shape != self.shape:
+            self.logger.dead("boundary mask has an incompatible shape")
+        self._boundary = np.ascontiguousarray(arr)
+        self._mask_touched = True
+
+    @property
+    def now(self) -> np.ndarray:
+        return self._host_view(0)
+
+    def __getitem__(self, key):
+        return self.now[key]
+
+    def __setitem__(self, key, value) -> None:
+        self.now[key] = value
+
+    def fill(self, data: np.ndarray, time: int = 0) -> None:
+        if data.shape != self.shape or data.dtype != self.numpy_dtype:
+            self.logger.dead("Unable to fill grid with incompatible shape or data type")
+        k = abs(time)
+        while len(self._ring) <= k:
+            self._ring.append(_Level())
+        lv = self._ring[k]
+        lv.host = np.ascontiguousarray(data).copy()
+        lv.where = "host"
+
+    @property
+    def _data(self) -> list:
+        """Host copies of every ring level, newest first (reference attribute)."""
+        return [self._host_view(k) for k in range(len(self._ring))]
+
+    # ------------------------------------------------------------------ ring (operator.py:37-39)
+    def _extend_time(self, depth: int) -> None:
+        while len(self._ring) < depth:
+            self._ring.append(_Level())
+        for lv in self._ring[depth:]:
+            self._release(lv)
+        del self._ring[depth:]
+
+    def _op_invoke(self, depth: int, tick: bool) -> None:
+        self._extend_time(depth)
+        if tick:
+            self._ring.insert(0, self._ring.pop())
+
+    # ------------------------------------------------------------------ host <-> device
+    def _runtime(self):
+        if self._rt is None:
+            from .runtime.shim import Runtime
+            self._rt = Runtime.get()
+        return self._rt
+
+    def _layout(self):
+        lead = (SLACK + self._ghost * self.stride0) * self.itemsize
+        lead = (lead + ALIGN - 1) // ALIGN * ALIGN
+        tail = (SLACK + self._ghost * self.stride0) * self.itemsize
+        return lead, lead + self.size * self.itemsize + tail
+
+    def _alloc_level(self, lv: _Level) -> None:
+        rt = self._runtime()
+        lead, total = self._layout()
+        raw = rt.alloc(total)          # zero-filled
+        self._allocs.append(raw)
+        lv.dev = raw + lead
+        lv.raw = raw
+
+    def _release(self, lv: _Level) -> None:
+        if lv.dev and self._rt is not None:
+            self._rt.free(lv.raw)
+            if lv.raw in self._allocs:
+                self._allocs.remove(lv.raw)
+        lv.dev = 0
+
+    def _host_view(self, k: int) -> np.ndarray:
+        lv = self._ring[k]
+        if lv.where == "zero":
+            lv.host = np.zeros(self.shape, self.numpy_dtype)
+        elif lv.where == "device":
+            if lv.host is None:
+                lv.host = np.empty(self.shape, self.numpy_dtype)
+            rt = self._runtime()
+            rt.d2h(lv.host.ctypes.data, lv.dev, self.size * self.itemsize)
+            rt.sync()
+        # the caller may write through the returned array: the host owns the level now
+        lv.where = "host"
+        return lv.host
+
+    def _to_device(self, lv: _Level) -> None:
+        if lv.dev == 0:
+            self._alloc_level(lv)
+            if lv.where == "zero":
+                lv.where = "device"
+                return
+        if lv.where == "host":
+            host = np.ascontiguousarray(lv.host)
+            self._runtime().h2d(lv.dev, host.ctypes.data, self.size * self.itemsize)
+            # pageable copies are staged synchronously by the driver; keep `host` alive anyway
+            lv.host = host
+        elif lv.where == "zero":
+            self._runtime().memset(lv.dev, 0, self.size * self.itemsize)
+        lv.where = "device"
+
+    def _ensure_ghost(self, rows: int) -> None:
+        if rows <= self._ghost:
+            return
+        # re-layout: pull everything to the host, drop device copies
+        for k in range(len(self._ring)):
+            if self._ring[k].where == "device":
+                self._host_view(k)
+        for lv in self._ring:
+            self._release(lv)
+        if self._scratch is not None:
+            self._release(self._scratch)
+            self._scratch = None
+        self._ghost = rows
+
+    def _prepare_device(self, ghost_rows: int = 1) -> None:
+        """Make every level and the mask resident before launches."""
+        self._ensure_ghost(ghost_rows)
+        for lv in self._ring:
+            if lv.where != "device":
+                self._to_device(lv)
+        if self._mask_touched:
+            self._upload_mask()
+
+    def _scratch_level(self) -> _Level:
+        if self._scratch is None or self._scratch.dev == 0:
+            self._scratch = _Level()
+            self._alloc_level(self._scratch)
+            self._scratch.where = "device"
+        return self._scratch
+
+    def _swap_scratch(self) -> None:
+        """Jacobi double buffer: the scratch level becomes level 0."""
+        self._ring[0], self._scratch = self._scratch, self._ring[0]
+        self._ring[0].where = "device"
+
+    # ------------------------------------------------------------------ mask compilation
+    def _upload_mask(self) -> None:
+        self._mask_touched = False
+        b = self._boundary
+        if self._mask_snapshot is not None and np.array_equal(b, self._mask_snapshot):
+            return
+        rt = self._runtime()
+        for ptr, _ in self._lists.values():
+            if ptr:
+                rt.free(ptr)
+        self._lists = {}
+        self._mask_snapshot = b.copy()
+        self._mask_version += 1
+        flat = b.reshape(-1)
+        self._mask_any = bool(flat.any())
+        if not self._mask_any:
+            return                      # all-zero class: kernels get null mask pointers
+        lo, hi = int(flat.min()), int(flat.max())
+        if lo < 0 or hi > 255:
+            self.logger.dead(f"boundary mask values must lie in [0, 255] on the B200 backend (got {lo}..{hi})")
+        m8 = flat.astype(np.uint8)
+        nchunk = (self.size + CHUNK - 1) // CHUNK
+        padded = np.zeros(nchunk * CHUNK, np.uint8)
+        padded[:self.size] = m8
+        flags = padded.reshape(nchunk, CHUNK).any(axis=1).astype(np.uint8)
+        if not self._mask_dev:
+            self._mask_dev = rt.alloc(nchunk * CHUNK)
+            self._flags_dev = rt.alloc(nchunk)
+        rt.h2d(self._mask_dev, padded.ctypes.data, padded.nbytes)
+        rt.h2d(self._flags_dev, flags.ctypes.data, flags.nbytes)
+        rt.sync()
+
+    def _mask_count(self, k: int) -> int:
+        if self._mask_snapshot is None:
+            return self.size if k == 0 else 0
+        return int(np.count_nonzero(self._mask_snapshot == k))
+
+    def _index_list(self, k: int):
+        """Device array of linear indices where boundary == k (cached per mask)."""
+        hit = self._lists.get(k)
+        if hit is None:
+            snap = self._mask_snapshot if self._mask_snapshot is not None else self._boundary
+            idx = np.flatnonzero(snap.reshape(-1) == k).astype(np.int64)
+            ptr = 0
+            if idx.size:
+                rt = self._runtime()
+                ptr = rt.alloc(idx.nbytes)
+                rt.h2d(ptr, idx.ctypes.data, idx.nbytes)
+                rt.sync()
+            hit = (ptr, int(idx.size))
+            self._lists[k] = hit
+        return hit
+
+    # ------------------------------------------------------------------ misc
+    def device_pointer(self, level: int = 0) -> int:
+        return self._ring[level].dev
+
+    def __del__(self) -> None:
+        try:
+            rt = self._rt
+            if rt is None:
+                return
+            for lv in self._ring:
+                self._release(lv)
+            if self._scratch is not None:
+                self._release(self._scratch)
+            for ptr, _ in self._lists.values():
+                if ptr:
+                    rt.free(ptr)
+            if self._mask_dev:
+                rt.free(self._mask_dev)
+                rt.free(self._flags_dev)
+        except Exception:
+            pass

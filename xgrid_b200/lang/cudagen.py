@@ -1,0 +1,482 @@
+"""Back end: sweep groups -> CUDA C for sm_100a.
+
+Replaces the reference's C99/OpenMP generator (xgrid/lang/generator.py:79-442).
+The reference emits, per stencil statement, a full-grid loop nest with a mask
+test (generator.py:289-304,353-361).  Here a *group* of statements is lowered
+to one ``__global__`` function assembled from the hand-written primitives in
+``csrc/templates/xgb_stencil.cuh``; this module only decides *what* is
+computed per point (expression text, which row windows are read, which slots
+are written) -- the ``how`` lives in the template header.
+
+Expression lowering follows generator.py:377-442: fully parenthesised C in
+source order, unsuffixed float literals (so fp32 programs keep the reference's
+mixed precision), ``**`` -> ``pow``/``powf`` by result type, with
+the literal exponent ``2.0`` emitted as a product because gcc folds it at the
+reference's optimisation levels (F7).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+from ..types import Boolean, Floating, Grid as GridT, Integer, Pointer, Structure, Value, Void
+from . import ir
+
+VARIANT_DENSE = "dense"
+VARIANT_SPARSE = "sparse"
+
+
+@dataclass
+class Slot:
+    """One (grid argument, ring level) buffer touched by a group.  ``level`` is
+    an int ring index, or "scratch" for the Jacobi double buffer that replaces
+    the reference's per-statement ``malloc`` (generator.py:321,351)."""
+    index: int
+    grid: str
+    level: object
+    elem: Value
+    read: bool = False
+    written: bool = False
+
+    @property
+    def field(self) -> str:
+        return f"s{self.index}"
+
+
+@dataclass
+class Group:
+    gid: int
+    ndim: int
+    stmts: list                                   # ir.Assignment with .sweep
+    slots: list = field(default_factory=list)     # Slot
+    masks: list = field(default_factory=list)     # grid names whose mask is consulted
+    scalars: dict = field(default_factory=dict)   # variable name -> type (by-value params)
+    shapes: list = field(default_factory=list)    # grid names whose shape() is queried
+    implicit: bool = False
+    sparse: bool = False                          # every statement runs on a mask value != 0
+    lead: str = ""                                # grid whose shape drives the sweep
+    name: str = ""
+    params_cls: type | None = None
+    vwidths: tuple = (1,)
+    halo0: int = 0                                # max |axis-0 offset| over all loads
+    halo_last: int = 0
+
+    def slot(self, grid: str, level) -> Slot:
+        for s in self.slots:
+            if s.grid == grid and s.level == level:
+                return s
+        raise KeyError((grid, level))
+
+
+class CodegenError(Exception):
+    pass
+
+
+# --------------------------------------------------------------------------- expressions
+class ExprEmitter:
+    """IR expression -> C text.  ``ident`` maps a scalar variable to its C
+    spelling; ``tap`` maps a Stencil load to its C spelling."""
+
+    def __init__(self, module: "ModuleBuilder", ident, tap=None) -> None:
+        self.module, self.ident, self.tap = module, ident, tap
+
+    def __call__(self, e) -> str:
+        return getattr(self, "x_" + type(e).__name__)(e)
+
+    def x_Constant(self, e: ir.Constant) -> str:
+        return repr(e.value).lower()            # generator.py:393-394
+
+    def x_Identifier(self, e: ir.Identifier) -> str:
+        return self.ident(e.variable)
+
+    def x_Access(self, e: ir.Access) -> str:
+        return f"({self(e.value)}).{e.attribute}"
+
+    def x_Unary(self, e: ir.Unary) -> str:
+        return f"({e.operator} {self(e.right)})"
+
+    def x_Binary(self, e: ir.Binary) -> str:
+        if e.operator == "^":
+            wide = isinstance(e.type, Floating) and e.type.width_bits == 64
+            base = self(e.left)
+            if isinstance(e.right, ir.Constant) and e.right.value == 2.0:
+                ctype = "double" if wide else "float"
+                return f"xgb::sq<{ctype}>({base})"
+            return f"{'pow' if wide else 'powf'}({base}, {self(e.right)})"
+        return f"({self(e.left)} {e.operator} {self(e.right)})"
+
+    def x_Condition(self, e: ir.Condition) -> str:
+        return f"({self(e.condition)} ? {self(e.body)} : {self(e.orelse)})"
+
+    def x_Cast(self, e: ir.Cast) -> str:
+        return f"(({self.module.ctype(e.type)})({self(e.value)}))"
+
+    def x_Stencil(self, e: ir.Stencil) -> str:
+        if self.tap is None:
+            raise CodegenError(f"grid access to '{e.variable.name}' outside a stencil statement")
+        return self.tap(e)
+
+    def x_GridInfo(self, e: ir.GridInfo) -> str:
+        if e.info == "dimension":
+            return str(e.variable.type.dimension)
+        return self.module.shape_ref(e.variable.name, self(e.dimension))
+
+    def x_Call(self, e: ir.Call) -> str:
+        args = ", ".join(self(a) for a in e.arguments)
+        if isinstance(e.operator, ir.Constructor):
+            return f"({self.module.ctype(e.operator.type)}{{{args}}})"
+        return f"{self.module.device_function(e.operator)}({args})"
+
+
+# --------------------------------------------------------------------------- module
+class ModuleBuilder:
+    """Accumulates one CUDA translation unit: struct definitions, ``__device__``
+    helpers for called operators, and one or more sweep kernels."""
+
+    def __init__(self, overstep: str = "none") -> None:
+        self.overstep = overstep
+        self.structs: dict[str, str] = {}
+        self.functions: dict[str, str] = {}
+        self.kernels: list[str] = []
+        self._shape_ref = None
+
+    # ---- types
+    def ctype(self, t) -> str:
+        if isinstance(t, Void):
+            return "void"
+        if isinstance(t, Structure):
+            if t.name not in self.structs:
+                self.structs[t.name] = ""      # reserve (recursive fields)
+                body = "".join(f"    {self.ctype(ft)} {fn};\n" for fn, ft in t.elements)
+                self.structs[t.name] = f"struct {t.name} {{\n{body}}};\n"
+            return t.name
+        if isinstance(t, (Boolean, Integer, Floating)):
+            return t.cname
+        if isinstance(t, Pointer):
+            return self.ctype(t.element) + "*"
+        raise CodegenError(f"type '{t}' has no device representation")
+
+    def shape_ref(self, grid: str, dim_text: str) -> str:
+        if self._shape_ref is None:
+            raise CodegenError("shape() is only available inside kernels")
+        return self._shape_ref(grid, dim_text)
+
+    # ---- callee operators become __device__ functions (generator.py:208-212,418-419)
+    def device_function(self, op) -> str:
+        if op.mode == "external":
+            raise CodegenError(f"external operator '{op.name}' cannot be called from device code")
+        cname = op.name.replace(".", "_")
+        if cname in self.functions:
+            return cname
+        self.functions[cname] = ""             # reserve (recursion)
+        d = op.ir
+        for _, t in d.signature.arguments:
+            if isinstance(t, GridT):
+                raise CodegenError(f"operator '{op.name}' takes a grid and cannot be inlined into a sweep")
+        args = ", ".join(f"{self.ctype(t)} {n}" for n, t in d.signature.arguments)
+        lines = [f"__device__ __forceinline__ {self.ctype(d.signature.return_type)} {cname}({args}) {{"]
+        for n, v in d.scope.items():
+            if n not in d.signature.argnames_map:
+                lines.append(f"    {self.ctype(v.type)} {n};")
+
+        def ident(var):
+            return f"(*{var.name})" if isinstance(var.type, Pointer) else var.name
+
+        emit = ExprEmitter(self, ident)
+        self._scalar_block(d.body, emit, lines, 1)
+        lines.append("}")
+        self.functions[cname] = "\n".join(lines) + "\n"
+        return cname
+
+    def _scalar_block(self, stmts, emit, out, ind) -> None:
+        pad = "    " * ind
+        for s in stmts:
+            if isinstance(s, ir.Assignment):
+                if s.sweep is not None:
+                    raise CodegenError("stencil statements inside called operators are not supported")
+                out.append(f"{pad}{emit(s.terminal)} = {emit(s.value)};")
+            elif isinstance(s, ir.Return):
+                out.append(f"{pad}return{'' if s.value is None else ' ' + emit(s.value)};")
+            elif isinstance(s, ir.Break):
+                out.append(f"{pad}break;")
+            elif isinstance(s, ir.Continue):
+                out.append(f"{pad}continue;")
+            elif isinstance(s, ir.If):
+                out.append(f"{pad}if ({emit(s.condition)}) {{")
+                self._scalar_block(s.body, emit, out, ind + 1)
+                if s.orelse:
+                    out.append(f"{pad}}} else {{")
+                    self._scalar_block(s.orelse, emit, out, ind + 1)
+                out.append(f"{pad}}}")
+            elif isinstance(s, ir.While):
+                out.append(f"{pad}while ({emit(s.condition)}) {{")
+                self._scalar_block(s.body, emit, out, ind + 1)
+                out.append(f"{pad}}}")
+            elif isinstance(s, ir.For):
+                v = s.variable.name
+                out.append(f"{pad}for ({v} = {emit(s.start)}; {v} < {emit(s.end)}; {v} += {emit(s.step)}) {{")
+                self._scalar_block(s.body, emit, out, ind + 1)
+                out.append(f"{pad}}}")
+            elif isinstance(s, ir.Evaluation):
+                out.append(f"{pad}{emit(s.value)};")
+            elif isinstance(s, ir.Inline):
+                out.append(f"{pad}{s.source}")
+            else:
+                raise CodegenError(f"unsupported statement {type(s).__name__} in device function")
+
+    # ---- final text
+    def source(self) -> str:
+        parts = ['#include "xgb_stencil.cuh"\n']
+        parts.extend(self.structs.values())
+        parts.extend(self.functions.values())
+        parts.extend(self.kernels)
+        return "\n".join(parts)
+
+
+# --------------------------------------------------------------------------- group analysis
+def analyse_group(g: Group, scope: dict) -> None:
+    """Fill slots / masks / scalars / halo extents of a group from its statements."""
+    def slot(grid, level, elem):
+        for s in g.slots:
+            if s.grid == grid and s.level == level:
+                return s
+        s = Slot(len(g.slots), grid, level, elem)
+        g.slots.append(s)
+        return s
+
+    for a in g.stmts:
+        sw = a.sweep
+        if sw.grid.name not in g.masks:
+            g.masks.append(sw.grid.name)
+        store_level = "scratch" if g.implicit else sw.store.level
+        slot(sw.grid.name, store_level, sw.grid.type.element).written = True
+        if g.implicit:
+            # unwritten points carry the old value through the double buffer
+            slot(sw.grid.name, 0, sw.grid.type.element).read = True
+        for ld in sw.loads:
+            slot(ld.variable.name, ld.level, ld.variable.type.element).read = True
+            g.halo0 = max(g.halo0, abs(ld.space_offset[0]) if g.ndim > 1 else 0)
+            g.halo_last = max(g.halo_last, abs(ld.space_offset[-1]))
+        for e in ir.walk_expr(a.value):
+            if isinstance(e, ir.Identifier):
+                v = e.variable
+                if isinstance(v.type, GridT):
+                    continue
+                g.scalars.setdefault(v.name, v.type)
+            elif isinstance(e, ir.GridInfo) and e.info == "shape":
+                if e.variable.name not in g.shapes:
+                    g.shapes.append(e.variable.name)
+    g.lead = g.stmts[0].sweep.grid.name
+    g.sparse = all(a.sweep.mask != 0 for a in g.stmts) and len(g.stmts) == 1
+
+
+def vector_widths(g: Group) -> tuple:
+    sizes = []
+    for s in g.slots:
+        if isinstance(s.elem, Structure):
+            return (1,)
+        sizes.append(s.elem.width_bytes)
+    big = max(sizes) if sizes else 8
+    base = max(1, 16 // big)
+    out = [1]
+    if base > 1:
+        out.append(base)
+    out.append(base * 2)
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------- params struct
+def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims: dict) -> tuple[str, type]:
+    """C text of the by-value parameter struct + its ctypes twin (same field
+    order; natural alignment on both sides)."""
+    c_fields, py_fields = [], []
+
+    def add(ctype_text, name, pytype):
+        c_fields.append(f"    {ctype_text} {name};")
+        py_fields.append((name, pytype))
+
+    for s in g.slots:
+        t = module.ctype(s.elem)
+        qual = "" if s.written else "const "
+        add(f"{qual}{t}* __restrict__" if not (s.read and s.written) else f"{t}*", s.field, ctypes.c_void_p)
+    for m in g.masks:
+        add("const uint8_t* __restrict__", f"m_{m}", ctypes.c_void_p)
+        add("const uint8_t* __restrict__", f"f_{m}", ctypes.c_void_p)
+    add("const int64_t* __restrict__", "list", ctypes.c_void_p)
+    add("int64_t", "count", ctypes.c_int64)
+    add("int64_t", "rows", ctypes.c_int64)
+    add("int64_t", "cols", ctypes.c_int64)
+    for a in range(g.ndim):
+        add("int64_t", f"n{a}", ctypes.c_int64)
+    for name in g.shapes:
+        nd = grid_ndims[name]
+        add(f"int32_t", f"shape_{name}[{nd}]", ctypes.c_int32 * nd)
+    # user scalars / structs, widest first to avoid padding surprises
+    def width(t):
+        return ctypes.sizeof(t.ctype) if isinstance(t, Structure) else t.width_bytes
+    for name, t in sorted(g.scalars.items(), key=lambda kv: -min(8, width(kv[1].element if isinstance(kv[1], Pointer) else kv[1]))):
+        vt = t.element if isinstance(t, Pointer) else t
+        add(module.ctype(vt), f"u_{name}", vt.ctype)
+    # ctypes cannot declare "name[N]" -- strip the suffix for the python twin
+    py_clean = [(n.split("[")[0], t) for n, t in py_fields]
+    cls = type(f"{g.name}_P", (ctypes.Structure,), {"_fields_": py_clean})
+    text = f"struct {g.name}_P {{\n" + "\n".join(c_fields) + "\n};\n"
+    return text, cls
+
+
+# --------------------------------------------------------------------------- kernels
+def _outer_offset_text(g: Group, outer: tuple) -> str:
+    """Linear element offset of an outer-axis tap (all axes but the last)."""
+    terms = []
+    for a, d in enumerate(outer):
+        if d == 0:
+            continue
+        # stride of axis a = product of extents of the axes after it
+        stride = " * ".join(f"p.n{b}" for b in range(a + 1, g.ndim))
+        terms.append(f"({d}LL) * {stride}")
+    return " + ".join(terms) if terms else "0"
+
+
+def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -> None:
+    """Append the parameter struct and every variant of the group's kernel."""
+    g.vwidths = vector_widths(g)
+    ptext, g.params_cls = build_params(g, module, scope, grid_ndims)
+    module.kernels.append(ptext)
+    module._shape_ref = lambda grid, dim: f"p.shape_{grid}[{dim}]"
+    try:
+        if module.overstep == "none":
+            for v in g.vwidths:
+                module.kernels.append(_emit_windowed(g, module, v, VARIANT_DENSE))
+            module.kernels.append(_emit_windowed(g, module, 1, VARIANT_SPARSE))
+        else:
+            module.kernels.append(_emit_general(g, module, VARIANT_DENSE))
+            module.kernels.append(_emit_general(g, module, VARIANT_SPARSE))
+            g.vwidths = (1,)
+    finally:
+        module._shape_ref = None
+
+
+def kernel_name(g: Group, variant: str, v: int) -> str:
+    return f"{g.name}_{variant}_v{v}"
+
+
+def _ident(var) -> str:
+    return f"p.u_{var.name}"
+
+
+def _emit_statements(g: Group, module: ModuleBuilder, tap, lines: list, vexpr: str) -> None:
+    """Per-point body: statement-at-a-time in program order, each predicated on
+    the stored grid's mask value (generator.py:297-298)."""
+    emit = ExprEmitter(module, _ident, tap)
+    for a in g.stmts:
+        sw = a.sweep
+        store_level = "scratch" if g.implicit else sw.store.level
+        s = g.slot(sw.grid.name, store_level)
+        rhs = emit(a.value)
+        lines.append(f"        if (m_{sw.grid.name}[{vexpr}] == {sw.mask}) {{ "
+                     f"o_{s.field}[{vexpr}] = {rhs}; wr_{s.field} |= 1u << {vexpr}; }}")
+        if g.implicit:
+            old = tap(ir.Stencil(a.location, sw.grid.type.element, "load", sw.grid, 0,
+                                 (0,) * g.ndim, 0))
+            lines.append(f"        else {{ o_{s.field}[{vexpr}] = {old}; wr_{s.field} |= 1u << {vexpr}; }}")
+
+
+def _emit_windowed(g: Group, module: ModuleBuilder, V: int, variant: str) -> str:
+    # windows: (slot index, outer offsets) -> [lo, hi] over the contiguous axis
+    windows: dict = {}
+
+    def need(slot: Slot, offsets: tuple) -> None:
+        key = (slot.index, tuple(offsets[:-1]))
+        lo, hi = windows.get(key, (0, 0))
+        windows[key] = (min(lo, offsets[-1]), max(hi, offsets[-1]))
+
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            need(g.slot(ld.variable.name, ld.level), ld.space_offset)
+        if g.implicit:
+            need(g.slot(a.sweep.grid.name, 0), (0,) * g.ndim)
+    wnames = {key: f"w{n}" for n, key in enumerate(windows)}
+
+    def tap(e: ir.Stencil) -> str:
+        slot = g.slot(e.variable.name, e.level)
+        key = (slot.index, tuple(e.space_offset[:-1]))
+        lo, _ = windows[key]
+        return f"{wnames[key]}[v + {e.space_offset[-1] - lo}]"
+
+    name = kernel_name(g, variant, V)
+    L = [f'extern "C" __global__ void __launch_bounds__(256) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int V = {V};")
+    if variant == VARIANT_DENSE:
+        L.append("    const xgb::Tile t = xgb::dense_tile<V>(p.rows, p.cols);")
+        L.append("    if (!t.active) return;")
+        L.append("    const int64_t base = t.row * p.cols + t.col;")
+        for m in g.masks:
+            L.append(f"    int m_{m}[V]; xgb::ld_mask<V>(p.m_{m}, p.f_{m}, base, m_{m});")
+    else:
+        L.append("    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;")
+        L.append("    if (tid >= p.count) return;")
+        L.append("    const int64_t base = p.list[tid];")
+        for m in g.masks:
+            L.append(f"    int m_{m}[V] = {{{g.stmts[0].sweep.mask}}};")
+    for key, (lo, hi) in windows.items():
+        slot = g.slots[key[0]]
+        t = module.ctype(slot.elem)
+        off = _outer_offset_text(g, key[1])
+        L.append(f"    {t} {wnames[key]}[V + {hi - lo}]; "
+                 f"xgb::ld_window<{t}, V, {lo}, {hi}>(p.{slot.field} + (base + {off}), {wnames[key]});")
+    for s in g.slots:
+        if s.written:
+            L.append(f"    {module.ctype(s.elem)} o_{s.field}[V]; unsigned wr_{s.field} = 0u;")
+    L.append("#pragma unroll")
+    L.append("    for (int v = 0; v < V; ++v) {")
+    _emit_statements(g, module, tap, L, "v")
+    L.append("    }")
+    for s in g.slots:
+        if s.written:
+            L.append(f"    xgb::st_pred<{module.ctype(s.elem)}, V>(p.{s.field} + base, o_{s.field}, wr_{s.field});")
+    L.append("}")
+    return "\n".join(L) + "\n"
+
+
+def _emit_general(g: Group, module: ModuleBuilder, variant: str) -> str:
+    """overstep = "limit" / "wrap": every tap is addressed through clamped /
+    wrapped per-axis coordinates (generator.py:172-177, with correct extents)."""
+    adj = "xgb::clamp_idx" if module.overstep == "limit" else "xgb::wrap_idx"
+
+    def tap(e: ir.Stencil) -> str:
+        slot = g.slot(e.variable.name, e.level)
+        coords = [f"{adj}(i{a} + ({d}), p.n{a})" for a, d in enumerate(e.space_offset)]
+        lin = coords[0]
+        for a in range(1, g.ndim):
+            lin = f"({lin}) * p.n{a} + {coords[a]}"
+        return f"p.{slot.field}[{lin}]"
+
+    name = kernel_name(g, variant, 1)
+    L = [f'extern "C" __global__ void __launch_bounds__(256) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append("    constexpr int V = 1;")
+    if variant == VARIANT_DENSE:
+        L.append("    const xgb::Tile t = xgb::dense_tile<V>(p.rows, p.cols);")
+        L.append("    if (!t.active) return;")
+        L.append("    const int64_t base = t.row * p.cols + t.col;")
+        for m in g.masks:
+            L.append(f"    int m_{m}[V]; xgb::ld_mask<V>(p.m_{m}, p.f_{m}, base, m_{m});")
+    else:
+        L.append("    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;")
+        L.append("    if (tid >= p.count) return;")
+        L.append("    const int64_t base = p.list[tid];")
+        for m in g.masks:
+            L.append(f"    int m_{m}[V] = {{{g.stmts[0].sweep.mask}}};")
+    L.append("    int64_t rem = base;")
+    for a in range(g.ndim - 1, -1, -1):
+        L.append(f"    const int64_t i{a} = rem % p.n{a}; rem /= p.n{a};")
+    for s in g.slots:
+        if s.written:
+            L.append(f"    {module.ctype(s.elem)} o_{s.field}[V]; unsigned wr_{s.field} = 0u;")
+    L.append("    { const int v = 0;")
+    _emit_statements(g, module, tap, L, "v")
+    L.append("    }")
+    for s in g.slots:
+        if s.written:
+            L.append(f"    xgb::st_pred<{module.ctype(s.elem)}, V>(p.{s.field} + base, o_{s.field}, wr_{s.field});")
+    L.append("}")
+    return "\n".join(L) + "\n"

@@ -1,0 +1,462 @@
+"""Kernel program: grouping, host control flow, launches.
+
+The reference turns a kernel into ONE C function: scalar prologue and control
+flow run serially on the calling thread and each stencil statement is an OpenMP
+loop nest in program order (xgrid/lang/generator.py:216-225,285-364;
+SURVEY.md §3d).  Here the same program order is kept, but
+
+* scalar statements and control flow are evaluated on the host by ``HostEval``
+  with C semantics (declared-width integers/floats, truncating ``/``,
+  dividend-signed ``%``, unsuffixed-literal doubles);
+* consecutive stencil statements that are provably independent point-wise are
+  fused into one *sweep group* = one launch of a generated sm_100a kernel;
+* statements that only touch a sparse boundary set (mask value != 0) run over
+  a compacted index list instead of scanning the whole grid;
+* Jacobi-style "implicit" statements (generator.py:312-352) write a per-grid
+  scratch level that is then pointer-swapped with level 0 -- no malloc/free and
+  no second copy sweep.
+
+A whole ``Operator.__call__`` is recorded once per (scalar arguments, buffer
+identities) into a CUDA graph and replayed afterwards.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import math
+import os
+from dataclasses import astuple, fields as dc_fields, is_dataclass
+
+import numpy as np
+
+from ..config import get_config
+from ..log import Logger
+from ..types import Boolean, Floating, Grid as GridT, Integer, Number, Pointer, Structure, Void
+from . import cudagen, ir
+
+_TEMPLATE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "templates")
+
+
+def template_headers() -> dict:
+    out = {}
+    for fn in sorted(os.listdir(_TEMPLATE_DIR)):
+        if fn.endswith(".cuh"):
+            with open(os.path.join(_TEMPLATE_DIR, fn)) as f:
+                out[fn] = f.read()
+    return out
+
+
+# --------------------------------------------------------------------------- plan nodes
+class GroupNode:
+    def __init__(self, group: cudagen.Group) -> None:
+        self.group = group
+
+
+def _reads_level0_of(stmt, grids: set) -> bool:
+    return any(ld.level == 0 and ld.variable.name in grids for ld in stmt.sweep.loads)
+
+
+def build_plan(stmts: list, groups: list, ndim_of) -> list:
+    """Replace runs of fusable stencil statements by GroupNodes (recursively)."""
+    plan: list = []
+    cur: list = []
+
+    def flush():
+        nonlocal cur
+        if cur:
+            g = cudagen.Group(len(groups), cur[0].sweep.grid.type.dimension, cur,
+                              implicit=cur[0].sweep.implicit)
+            groups.append(g)
+            plan.append(GroupNode(g))
+            cur = []
+
+    def can_join(s) -> bool:
+        if not cur:
+            return True
+        if s.sweep.implicit or cur[0].sweep.implicit:
+            return False
+        if s.sweep.grid.type.dimension != cur[0].sweep.grid.type.dimension:
+            return False
+        stored = {a.sweep.grid.name for a in cur}
+        if any((a.sweep.grid.name, a.sweep.mask) == (s.sweep.grid.name, s.sweep.mask) for a in cur):
+            return False
+        if s.sweep.store.level != 0 or any(a.sweep.store.level != 0 for a in cur):
+            return False
+        # flow dependence: s reads a level-0 buffer some earlier member writes
+        if _reads_level0_of(s, stored):
+            return False
+        # anti dependence: an earlier member reads level 0 of what s writes
+        if any(_reads_level0_of(a, {s.sweep.grid.name}) for a in cur):
+            return False
+        # a sparse (mask != 0) statement that reads its own level 0 stays alone
+        if _reads_level0_of(s, {s.sweep.grid.name}):
+            return False
+        return True
+
+    for s in stmts:
+        if isinstance(s, ir.Assignment) and s.sweep is not None:
+            if not can_join(s):
+                flush()
+            cur.append(s)
+            if s.sweep.implicit or _reads_level0_of(s, {s.sweep.grid.name}):
+                flush()
+            continue
+        flush()
+        if isinstance(s, ir.If):
+            plan.append(("if", s, build_plan(s.body, groups, ndim_of), build_plan(s.orelse, groups, ndim_of)))
+        elif isinstance(s, ir.While):
+            plan.append(("while", s, build_plan(s.body, groups, ndim_of)))
+        elif isinstance(s, ir.For):
+            plan.append(("for", s, build_plan(s.body, groups, ndim_of)))
+        else:
+            plan.append(("stmt", s))
+    flush()
+    return plan
+
+
+# --------------------------------------------------------------------------- host evaluator
+class _Return(Exception):
+    def __init__(self, value) -> None:
+        self.value = value
+
+
+class _Break(Exception):
+    pass
+
+
+class _Continue(Exception):
+    pass
+
+
+def np_type(t):
+    if isinstance(t, Boolean):
+        return np.bool_
+    return t.np_dtype
+
+
+def coerce(t, value):
+    """Convert a Python / numpy value to the C object type ``t``."""
+    if isinstance(t, Structure):
+        return value
+    if isinstance(t, Integer):
+        half = 1 << (t.width_bits - 1)
+        return np_type(t)((int(value) + half) % (2 * half) - half)   # two's-complement wrap
+    return np_type(t)(value)
+
+
+class HostEval:
+    """Evaluates scalar IR with C semantics (the host half of a kernel)."""
+
+    def __init__(self, env: dict, grids: dict) -> None:
+        self.env = env          # name -> numpy scalar | dataclass | ctypes pointer target
+        self.grids = grids
+
+    def __call__(self, e):
+        return getattr(self, "v_" + type(e).__name__)(e)
+
+    def v_Constant(self, e):
+        v = e.value
+        if type(v) is bool:
+            return np.bool_(v)
+        if type(v) is int:
+            return np.int32(v)
+        return np.float64(v)        # unsuffixed literal: a C double
+
+    def v_Identifier(self, e):
+        val = self.env[e.variable.name]
+        if isinstance(e.variable.type, Pointer):
+            return coerce(e.variable.type.element, _deref(val))
+        return val
+
+    def v_Access(self, e):
+        base = self(e.value)
+        return coerce(e.type, getattr(base, e.attribute))
+
+    def v_Unary(self, e):
+        r = self(e.right)
+        if e.operator == "!":
+            return np.bool_(not bool(r))
+        if e.operator == "-":
+            with np.errstate(all="ignore"):
+                return -r
+        return +r
+
+    def v_Binary(self, e):
+        op = e.operator
+        if op == "&&":
+            return np.bool_(bool(self(e.left)) and bool(self(e.right)))
+        if op == "||":
+            return np.bool_(bool(self(e.left)) or bool(self(e.right)))
+        a, b = self(e.left), self(e.right)
+        with np.errstate(all="ignore"):
+            if op == "+":
+                return a + b
+            if op == "-":
+                return a - b
+            if op == "*":
+                return a * b
+            if op == "/":
+                if isinstance(a, np.integer) and isinstance(b, np.integer):
+                    if int(b) == 0:
+                        raise ZeroDivisionError("integer division by zero in kernel scalar code")
+                    q = abs(int(a)) // abs(int(b))
+                    return type(a)(q if (int(a) < 0) == (int(b) < 0) else -q)
+                return a / b
+            if op == "%":
+                if isinstance(a, np.integer) and isinstance(b, np.integer):
+                    return type(a)(math.fmod(int(a), int(b)))
+                raise Exception("operator % on floating operands is not valid C")
+            if op == "^":
+                wide = isinstance(e.type, Floating) and e.type.width_bits == 64
+                if isinstance(e.right, ir.Constant) and e.right.value == 2.0:
+                    x = np.float64(a) if wide else np.float32(a)
+                    return x * x
+                if wide:
+                    return np.float64(math.pow(float(a), float(b)))
+                return np.float32(np.float32(a) ** np.float32(b))
+            return np.bool_({"==": a == b, "!=": a != b, ">": a > b, ">=": a >= b,
+                             "<": a < b, "<=": a <= b}[op])
+
+    def v_Condition(self, e):
+        return self(e.body) if bool(self(e.condition)) else self(e.orelse)
+
+    def v_Cast(self, e):
+        v = self(e.value)
+        if isinstance(e.type, Integer) and isinstance(v, np.floating):
+            v = math.trunc(float(v))
+        return coerce(e.type, v)
+
+    def v_GridInfo(self, e):
+        g = self.grids[e.variable.name]
+        if e.info == "dimension":
+            return np.int32(len(g.shape))
+        return np.int32(g.shape[int(self(e.dimension))])
+
+    def v_Stencil(self, e):
+        raise Exception(f"grid access to '{e.variable.name}' outside a stencil statement")
+
+    def v_Call(self, e):
+        args = [self(a) for a in e.arguments]
+        if isinstance(e.operator, ir.Constructor):
+            st = e.operator.type
+            return st.dataclass(*[_to_py(a) for a in args])
+        return call_scalar_operator(e.operator, args, self.grids)
+
+
+def _to_py(v):
+    return v.item() if isinstance(v, np.generic) else v
+
+
+def _deref(p):
+    if hasattr(p, "contents"):
+        return p.contents.value
+    return p.value
+
+
+def _store_ptr(p, v):
+    if hasattr(p, "contents"):
+        p.contents.value = _to_py(v)
+    else:
+        p.value = _to_py(v)
+
+
+def call_scalar_operator(op, args, grids):
+    """Interpret a called ``@function`` / ``@kernel`` operator whose body is
+    scalar-only (the reference compiles it into the same TU,
+    generator.py:208-212)."""
+    if op.mode == "external":
+        raise Exception(f"external operator '{op.name}' has no host implementation")
+    d = op.ir
+    env = {}
+    for (n, t), v in zip(d.signature.arguments, args):
+        env[n] = v
+    runner = _Interpreter(d, env, grids, launcher=None)
+    return runner.run(build_plan(d.body, [], None))
+
+
+class _Interpreter:
+    def __init__(self, definition, env, grids, launcher) -> None:
+        self.d, self.env, self.grids, self.launcher = definition, env, grids, launcher
+        self.ev = HostEval(env, grids)
+
+    def run(self, plan):
+        try:
+            self.block(plan)
+        except _Return as r:
+            return r.value
+        return None
+
+    def block(self, plan) -> None:
+        for node in plan:
+            if isinstance(node, GroupNode):
+                if self.launcher is None:
+                    raise Exception("stencil statements inside called operators are not supported")
+                self.launcher(node.group, self.env)
+                continue
+            kind = node[0]
+            if kind == "stmt":
+                self.statement(node[1])
+            elif kind == "if":
+                self.block(node[2] if bool(self.ev(node[1].condition)) else node[3])
+            elif kind == "while":
+                while bool(self.ev(node[1].condition)):
+                    try:
+                        self.block(node[2])
+                    except _Break:
+                        break
+                    except _Continue:
+                        continue
+            elif kind == "for":
+                s = node[1]
+                name, t = s.variable.name, s.variable.type
+                self.env[name] = coerce(t, self.ev(s.start))
+                while bool(self.env[name] < self.ev(s.end)):
+                    try:
+                        self.block(node[2])
+                    except _Break:
+                        break
+                    except _Continue:
+                        pass
+                    with np.errstate(all="ignore"):
+                        self.env[name] = coerce(t, self.env[name] + self.ev(s.step))
+
+    def statement(self, s) -> None:
+        if isinstance(s, ir.Assignment):
+            value = self.ev(s.value)
+            self.assign(s.terminal, value)
+        elif isinstance(s, ir.Return):
+            raise _Return(None if s.value is None else self.ev(s.value))
+        elif isinstance(s, ir.Break):
+            raise _Break()
+        elif isinstance(s, ir.Continue):
+            raise _Continue()
+        elif isinstance(s, ir.Evaluation):
+            self.ev(s.value)
+        elif isinstance(s, ir.Inline):
+            raise Exception("`with xgrid.c()` inline text is host C in the reference; the B200 backend "
+                            "cannot execute it (SURVEY.md §8f rank 2)")
+        else:
+            raise Exception(f"unsupported statement {type(s).__name__}")
+
+    def assign(self, target, value) -> None:
+        if isinstance(target, ir.Identifier):
+            var = target.variable
+            if isinstance(var.type, Pointer):
+                _store_ptr(self.env[var.name], coerce(var.type.element, value))
+            else:
+                self.env[var.name] = coerce(var.type, value)
+        elif isinstance(target, ir.Access):
+            base = self.ev(target.value)
+            setattr(base, target.attribute, _to_py(coerce(target.type, value)))
+        else:
+            raise Exception("unsupported assignment target")
+
+
+# --------------------------------------------------------------------------- Program
+class Program:
+    """A compiled kernel: plan + generated module + launch logic."""
+
+    _serial = 0
+
+    def __init__(self, op) -> None:
+        self.op = op
+        self.logger = Logger(self)
+        self.config = get_config()
+        self.ir = op.ir
+        self.depth = self.ir.depth
+        self.groups: list[cudagen.Group] = []
+        self.plan = build_plan(self.ir.body, self.groups, None)
+        self.grid_args = [(n, t) for n, t in self.ir.signature.arguments if isinstance(t, GridT)]
+        self.grid_ndims = {n: t.dimension for n, t in self.grid_args}
+        Program._serial += 1
+        tag = "".join(ch if ch.isalnum() else "_" for ch in op.name)
+        self.module_builder = cudagen.ModuleBuilder(self.config.overstep)
+        scope_types = {n: v.type for n, v in self.ir.scope.items()}
+        for g in self.groups:
+            g.name = f"xg_{tag}_g{g.gid}"
+            cudagen.analyse_group(g, scope_types)
+            cudagen.emit_group(g, self.module_builder, scope_types, self.grid_ndims)
+        self.source = self.module_builder.source() if self.groups else ""
+        self._module = None
+        self._functions: dict = {}
+        self._graphs: dict = {}
+        self._image = None
+
+    # ---- JIT (replaces Compiler.compile's md5 cache, xgrid/util/ffi.py:67-85)
+    def image(self) -> bytes:
+        if self._image is None:
+            from ..runtime import shim
+            headers = template_headers()
+            flags = self.config.nvrtc_flags
+            key = hashlib.sha256("\0".join([self.source, *flags, *headers.values()]).encode()).hexdigest()[:32]
+            root = os.path.join(".", self.config.cacheroot)
+            os.makedirs(root, exist_ok=True)
+            cu, cubin = os.path.join(root, key + ".cu"), os.path.join(root, key + ".cubin")
+            if os.path.exists(cubin) and os.path.exists(cu):
+                with open(cubin, "rb") as f:
+                    self._image = f.read()
+                self.logger.info(f"jit loaded '{cubin}' from cache")
+            else:
+                self._image, log = shim.compile_cuda(self.source, self.op.name + ".cu", flags, headers)
+                with open(cu, "w") as f:
+                    f.write("// nvrtc " + " ".join(flags) + "\n" + self.source)
+                tmp = cubin + f".{os.getpid()}.tmp"
+                with open(tmp, "wb") as f:
+                    f.write(self._image)
+                os.replace(tmp, cubin)
+                self.logger.info(f"jit compiled '{cu}' to '{cubin}'")
+        return self._image
+
+    def function(self, name: str) -> int:
+        fn = self._functions.get(name)
+        if fn is None:
+            from ..runtime.shim import Runtime
+            rt = Runtime.get()
+            if self._module is None:
+                self._module = rt.module_load(self.image())
+            fn = rt.get_function(self._module, name)
+            self._functions[name] = fn
+        return fn
+
+    # ---- call
+    def __call__(self, *args):
+        sig = self.ir.signature.arguments
+        if len(args) != len(sig):
+            # xgrid/util/ffi.py:31-33
+            raise TypeError(f"this function takes {len(sig)} argument ({len(args)} given)")
+        from ..grid import Grid
+        env, grids = {}, {}
+        for (name, t), a in zip(sig, args):
+            if isinstance(t, GridT):
+                if not isinstance(a, Grid):
+                    raise TypeError(f"argument '{name}' must be an xgrid.Grid")
+                if a.dimension != t.dimension or a.element != t.element:
+                    raise TypeError(f"argument '{name}' expects {t!r}, got Grid({a.dimension}) of {a.element!r}")
+                grids[name] = a
+            elif isinstance(t, Pointer):
+                env[name] = a
+            elif isinstance(t, Structure):
+                if not is_dataclass(a):
+                    raise TypeError(f"argument '{name}' expects dataclass {t.name}")
+                env[name] = a
+            else:
+                env[name] = coerce(t, a)
+        # tick the field and resize the time ring (xgrid/lang/operator.py:37-39)
+        seen = set()
+        for g in grids.values():
+            if id(g) not in seen:
+                g._op_invoke(self.depth, self.op.tick)
+                seen.add(id(g))
+        for g in grids.values():
+            g._prepare_device()
+
+        from .launch import Launcher
+        launcher = Launcher(self, grids)
+        result = _Interpreter(self.ir, env, grids, launcher).run(self.plan)
+        launcher.finish()
+        rt = self.ir.signature.return_type
+        if isinstance(rt, Void) or result is None:
+            return None
+        if isinstance(rt, Structure):
+            return result
+        return _to_py(coerce(rt, result))
