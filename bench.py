@@ -254,7 +254,7 @@ def run_ours(args, rank: int, world: int):
     # ---- end to end through the public API (`e2e`): host IC -> K steps -> host result ----
     e2e = None
     offload = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         Ke = K
         t0 = time.perf_counter()
         g2 = fresh_grids()                     # host writes of IC + mask (pageable NumPy)
@@ -321,6 +321,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

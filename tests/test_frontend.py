@@ -1,0 +1,230 @@
+"""Front end / scheduler facts, checked on CPU: the DSL surface of SURVEY.md
+§8 a-1..a-3 (time defaults, masks, implicit detection, depth, errors), sweep
+grouping, and that every workload lowers to CUDA C that NVRTC accepts for
+sm_100a."""
+import ctypes
+from dataclasses import dataclass
+from typing import cast
+
+import numpy as np
+import pytest
+
+import xgrid_b200 as xgrid
+from xgrid_b200 import workloads as W
+from xgrid_b200.lang import ir
+from xgrid_b200.lang.schedule import Program, HostEval, call_scalar_operator
+
+TEMP = 10
+
+
+@pytest.fixture(autouse=True)
+def _init(tmp_path):
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+
+
+def sweeps(op):
+    return [s for s in ir.walk_stmts(op.ir.body) if isinstance(s, ir.Assignment) and s.sweep is not None]
+
+
+def test_time_defaults_and_depth():
+    k = W.make_kernels()
+    sw = sweeps(k["convection_1d"])
+    assert [s.sweep.mask for s in sw] == [0, 1]
+    store, loads = sw[0].sweep.store, sw[0].sweep.loads
+    assert store.time_offset == 0 and all(l.time_offset == -1 for l in loads)      # parser.py:523
+    assert sorted(l.space_offset for l in loads) == [(-1,), (0,), (0,)]
+    assert k["convection_1d"].ir.depth == 2
+    assert k["fill4"].ir.depth == 1                                                 # no loads -> one level
+    assert not any(s.sweep.implicit for s in sw)
+
+
+def test_explicit_time_sign_is_dropped():
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def two_back(u: f1) -> None:
+        u[0] = u[0][2] + u[1][-2]
+
+    assert two_back.ir.depth == 3
+    assert {l.level for l in sweeps(two_back)[0].sweep.loads} == {2}                # generator.py:428,432
+
+
+def test_cavity_structure():
+    k = W.make_kernels()
+    sw = sweeps(k["cavity_kernel"])
+    assert len(sw) == 16                      # b, p, 4 bc, (jacobi + 4 bc) in the loop, u, v, 3 bc
+    implicit = [s for s in sw if s.sweep.implicit]
+    assert len(implicit) == 1 and implicit[0].sweep.grid.name == "p"                # generator.py:67-68
+    # boundary statements that read level 0 of their own grid are NOT implicit (mask != 0)
+    neumann = [s for s in sw if s.sweep.mask in (1, 2, 3) and s.sweep.grid.name == "p"]
+    assert neumann and not any(s.sweep.implicit for s in neumann)
+    prog = Program(k["cavity_kernel"])
+    kinds = [(len(g.stmts), g.implicit, g.sparse) for g in prog.groups]
+    # b | p-first | 4 sparse BCs | Jacobi | 4 sparse BCs | fused tail (u, v, 3 Dirichlet BCs)
+    assert kinds[0] == (1, False, False) and kinds[1] == (1, False, False)
+    assert kinds[6] == (1, True, False)
+    assert kinds[-1] == (5, False, False)
+    assert sum(1 for kd in kinds if kd[2]) == 8
+
+
+def test_fusion_rules():
+    k = W.make_kernels()
+    for name in ("convection_1d", "diffusion_1d", "convection_2d", "diffusion_2d", "heat_3d"):
+        prog = Program(k[name])
+        assert len(prog.groups) == 1 and len(prog.groups[0].stmts) == 2, name       # interior + Dirichlet BC fused
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def dependent(u: f1, v: f1) -> None:
+        u[0] = v[0] * 2.0
+        v[0] = u[1][0]            # reads level 0 of u written above -> must not fuse
+
+    assert len(Program(dependent).groups) == 2
+
+
+def test_errors_are_plain_exceptions():
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def bad_mix(u: f1, n: int) -> None:
+        u[0] = u[0] + n                      # no implicit int -> float conversion (parser.py:374-376)
+
+    with pytest.raises(Exception, match="Incompatible binary operator"):
+        bad_mix.ir
+
+    @xgrid.kernel()
+    def bad_boundary(u: f1) -> None:
+        with xgrid.boundary(1.5):
+            u[0] = 1.0
+
+    with pytest.raises(Exception, match="boundary"):
+        bad_boundary.ir
+
+    @xgrid.kernel()
+    def load_outside(u: f1) -> float:
+        return u[0]
+
+    with pytest.raises(Exception, match="without stencil context"):
+        load_outside.ir
+
+    @xgrid.kernel()
+    def wrong_rank(u: f1) -> None:
+        u[0, 0] = 1.0
+
+    with pytest.raises(Exception, match="subscript length"):
+        wrong_rank.ir
+
+
+def test_stale_two_argument_boundary_form_is_accepted():
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def conv(u: f1, c: float) -> None:
+        u[0] = u[0] - c * (u[0] - u[-1])
+        with xgrid.boundary(u, 1):           # test.py:217 form
+            u[0] = 1.0
+
+    assert [s.sweep.mask for s in sweeps(conv)] == [0, 1]
+
+
+def test_arity_is_type_error():
+    k = W.make_kernels()
+    with pytest.raises(TypeError):
+        k["convection_1d"](xgrid.Grid((8,), float))
+
+
+@dataclass
+class Vector3i:
+    x: int
+    y: int
+    z: int
+
+    @xgrid.function(method=True)
+    def dot(self, b: "Vector3i") -> int:
+        return self.x * b.x + self.y * b.y + self.z * b.z
+
+
+def test_scalar_kernels_match_reference(golden):
+    """test.py:130-165 + a control-flow kernel; values from the real reference."""
+    g = golden("scalars")
+
+    @xgrid.kernel()
+    def add3(a: int, b: int) -> int:
+        return a + b + TEMP
+
+    @xgrid.kernel()
+    def vdot(a: Vector3i, b: Vector3i) -> int:
+        return a.dot(b)
+
+    @xgrid.kernel()
+    def scal(a: float, b: float, n: int) -> float:
+        acc = 0.0
+        for i in range(0, n):
+            if i % 2 == 0:
+                acc = acc + a / b
+            else:
+                acc = acc - a * b ** 2.0
+        return acc
+
+    assert add3(123, 456) == int(g["add3"])
+    assert vdot(Vector3i(1, -2, 3), Vector3i(4, 5, -6)) == int(g["vdot"])
+    assert scal(1.7, 0.3, 9) == float(g["scal"])
+
+
+def test_c_integer_semantics():
+    @xgrid.kernel()
+    def idiv(a: int, b: int) -> int:
+        return a / b + a % b
+
+    assert idiv(-7, 2) == -3 + -1            # C truncation and dividend-signed remainder
+    assert idiv(7, -2) == -3 + 1
+
+    @xgrid.kernel()
+    def casts(x: float) -> int:
+        return cast(int, x) + cast(int, 0.0 - x)
+
+    assert casts(2.75) == 2 + -2
+
+
+def test_ptr_arguments():
+    @xgrid.kernel()
+    def bump(p: xgrid.ptr[int], by: int) -> None:
+        p = p + by
+
+    v = ctypes.c_int32(5)
+    bump(ctypes.pointer(v), 3)
+    assert v.value == 8
+
+
+def test_every_workload_compiles_for_sm100a():
+    from xgrid_b200.runtime import shim
+    for name, op in W.make_kernels().items():
+        prog = Program(op)
+        if not prog.groups:
+            continue
+        image = prog.image()
+        assert image[:4] == b"\x7fELF", name
+        for g in prog.groups:
+            assert ctypes.sizeof(g.params_cls) <= 4096      # by-value kernel parameter limit
+
+
+def test_fp32_mode_keeps_double_literals():
+    xgrid.init(cacheroot=".xgrid_test_f32")          # precision="float"
+    k = W.make_kernels()
+    src = Program(k["diffusion_1d"]).source
+    assert "float" in src and "2.0 *" in src and "2.0f" not in src
+    assert "xgb::sq<float>" in src                                      # ** 2.0 -> product (F7), powf type
+    import shutil
+    shutil.rmtree(".xgrid_test_f32", ignore_errors=True)
+
+
+def test_ring_semantics_on_host_only():
+    """Ring rotation / truncation are host bookkeeping: no GPU needed."""
+    g = xgrid.Grid((6,), float)
+    g.now[:] = np.arange(6)
+    g._op_invoke(2, True)
+    assert len(g._ring) == 2 and not g.now.any() and np.array_equal(g._data[1], np.arange(6))
+    g._op_invoke(3, True)
+    assert len(g._ring) == 3
+    g._op_invoke(1, False)
+    assert len(g._ring) == 1

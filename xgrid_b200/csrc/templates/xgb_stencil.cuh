@@ -135,6 +135,31 @@ XGB_DEV void ld_window_shfl(const T *row, T (&w)[V + HI - LO]) {
     }
 }
 
+// Window assembled from a register-resident body: w[k] = row[LO + k].  The
+// fringes come from the neighbouring lanes' bodies by warp shuffle; the lanes
+// on a warp edge (or at the end of a grid row) read them from global memory
+// instead.  Must be executed by all 32 lanes (no divergence around it); lanes
+// own consecutive V-element bodies of the same row.
+template <class T, int V, int LO, int HI>
+XGB_DEV void window_from_body(const T *row, const T (&body)[V], bool edge_l, bool edge_r,
+                              T (&w)[V + HI - LO]) {
+    static_assert(LO <= 0 && HI >= 0 && -LO <= V && HI <= V, "fringe wider than the body");
+#pragma unroll
+    for (int i = 0; i < V; ++i) w[i - LO] = body[i];
+#pragma unroll
+    for (int k = LO; k < 0; ++k) {
+        T x = __shfl_up_sync(0xffffffffu, body[V + k], 1);
+        if (edge_l) x = row[k];
+        w[k - LO] = x;
+    }
+#pragma unroll
+    for (int k = 0; k < HI; ++k) {
+        T x = __shfl_down_sync(0xffffffffu, body[k], 1);
+        if (edge_r) x = row[V + k];
+        w[V - LO + k] = x;
+    }
+}
+
 // Store v[i] where bit i of `written` is set (points whose mask matched no
 // statement keep the ring buffer's previous content).
 template <class T, int V>
@@ -157,6 +182,88 @@ XGB_DEV void ld_mask(const uint8_t *mask, const uint8_t *flags, int64_t base, in
     for (int i = 0; i < V; ++i) m[i] = 0;
     if (mask == nullptr) return;
     if (flags != nullptr && flags[base >> XGB_CHUNK_SHIFT] == 0) return;
+    if constexpr (V == 1) {
+        m[0] = mask[base];
+    } else {
+        uint8_t b[V];
+        ld_vec<uint8_t, V>(mask + base, b);
+#pragma unroll
+        for (int i = 0; i < V; ++i) m[i] = b[i];
+    }
+}
+
+// --------------------------------------------------------------------------- async tile pipeline
+// sm_100a bulk-copy pipeline for the "tiled" sweep variant: one producer lane
+// streams halo'd planes of every input level into a ring of shared-memory stages
+// with cp.async.bulk (the TMA engine's linear mode -- SASS UBLKCP) completing on
+// an mbarrier; consumer warps wait on the "full" barrier, compute one output plane
+// from shared memory and release the oldest plane through the "empty" barrier.
+// Bytes in flight live in shared memory, not in registers, so occupancy does not
+// pay for memory-level parallelism.
+namespace pipe {
+
+XGB_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+XGB_DEV void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+XGB_DEV void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+XGB_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+XGB_DEV void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+XGB_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "XGB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra XGB_DONE;\n"
+        "bra XGB_WAIT;\n"
+        "XGB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both sides 16-B aligned)
+XGB_DEV void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace pipe
+
+// window from a shared-memory row: w[k] = row[LO + k]; `row` points at the thread's
+// body (16-B aligned), fringes are scalar LDS.
+template <class T, int V, int LO, int HI>
+XGB_DEV void lds_window(const T *row, T (&w)[V + HI - LO]) {
+    T body[V];
+    ld_vec<T, V>(row, body);
+#pragma unroll
+    for (int i = 0; i < V; ++i) w[i - LO] = body[i];
+#pragma unroll
+    for (int k = LO; k < 0; ++k) w[k - LO] = row[k];
+#pragma unroll
+    for (int k = 0; k < HI; ++k) w[V - LO + k] = row[V + k];
+}
+
+// Mask fetch split in two so that the (global) flag byte can be requested one
+// plane ahead of its use: ld_flag() early, ld_mask_flagged() at the point of use.
+XGB_DEV int ld_flag(const uint8_t *mask, const uint8_t *flags, int64_t base) {
+    if (mask == nullptr) return 0;
+    if (flags == nullptr) return 1;
+    return flags[base >> XGB_CHUNK_SHIFT];
+}
+template <int V>
+XGB_DEV void ld_mask_flagged(const uint8_t *mask, int flag, int64_t base, int (&m)[V]) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) m[i] = 0;
+    if (flag == 0) return;
     if constexpr (V == 1) {
         m[0] = mask[base];
     } else {

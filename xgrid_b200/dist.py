@@ -1,0 +1,145 @@
+"""Slab decomposition and halo exchange (one process per GPU).
+
+New work with no counterpart in the reference, which is single-address-space
+OpenMP only.  Every statement of the DSL is a point-wise
+map with literal relative offsets, so a grid is split into contiguous slabs
+along axis 0; rank r owns rows ``slab_range(n0, r, P)`` plus ``ghost`` rows on
+either side of every time level.  The ghost rows are exactly the zero rows a
+single-GPU level already carries (xgrid_b200/grid.py), so kernels are
+unchanged: on a sharded grid the launcher refreshes them from the neighbours
+before a sweep reads a level at a non-zero axis-0 offset, and only if that
+level was written (or uploaded) since its last exchange.
+
+Transport: NCCL ``ncclSend/ncclRecv`` grouped per exchange and enqueued on the
+compute stream through the C ABI (``xgb_halo_exchange``); the NCCL unique id is
+distributed through ``torch.distributed``'s store.  The planner and partition
+logic are transport-agnostic (tests drive them over gloo on CPU).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .log import Logger
+
+_log = Logger("xgrid.dist")
+
+
+def slab_range(n0: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [lo, hi) of axis 0 owned by ``rank`` (remainder spread over the first ranks)."""
+    base, rem = divmod(n0, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Topology:
+    """Open chain of ranks along axis 0 (overstep 'none' / 'limit')."""
+
+    def __init__(self, rank: int, world: int) -> None:
+        self.rank, self.world = rank, world
+        self.lo_rank = rank - 1 if rank > 0 else -1
+        self.hi_rank = rank + 1 if rank < world - 1 else -1
+
+    @property
+    def sharded(self) -> bool:
+        return self.world > 1
+
+
+_topology: Topology | None = None
+_transport = None
+
+
+def topology() -> Topology:
+    """Process topology: from torch.distributed when initialised, else single rank."""
+    global _topology
+    if _topology is None:
+        rank, world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        _topology = Topology(rank, world)
+    return _topology
+
+
+def reset() -> None:
+    global _topology, _transport
+    _topology, _transport = None, None
+
+
+class HaloPlan:
+    """Which levels need their ghost rows refreshed before a group runs.
+
+    ``needs(group_slots, levels)`` is pure bookkeeping: a level is stale when it
+    has been written or uploaded since its last exchange (``_Level.halo_ok``)."""
+
+    @staticmethod
+    def stale(reads: list) -> list:
+        """reads: [(grid, level_object, halo_rows)] -> the subset to exchange."""
+        out, seen = [], set()
+        for grid, lv, h in reads:
+            if h <= 0 or not getattr(grid, "sharded", False):
+                continue
+            if getattr(lv, "halo_ok", False) or id(lv) in seen:
+                continue
+            seen.add(id(lv))
+            out.append((grid, lv, h))
+        return out
+
+
+class NcclTransport:
+    """ncclSend/ncclRecv neighbour exchange through the C ABI (xgb_halo_exchange)."""
+
+    def __init__(self, topo: Topology) -> None:
+        from .runtime import shim
+        import torch.distributed as dist
+        self.topo = topo
+        self.shim = shim
+        self.rt = shim.Runtime.get()
+        lib = shim.lib()
+        nccl_path = ""
+        try:
+            import nvidia.nccl
+            cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                nccl_path = cand
+        except ImportError:
+            pass
+        shim.check(lib.xgb_nccl_load(nccl_path.encode()))
+        store = dist.distributed_c10d._get_default_store()
+        key = "xgrid_b200/nccl_id"
+        if topo.rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            shim.check(lib.xgb_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+            store.set(key, buf.raw)
+        raw = store.get(key)
+        buf = ctypes.create_string_buffer(bytes(raw), 128)
+        shim.check(lib.xgb_nccl_init(ctypes.cast(buf, ctypes.c_void_p), topo.rank, topo.world))
+        _log.info(f"NCCL halo transport ready: rank {topo.rank}/{topo.world}")
+
+    def exchange(self, items: list, stream: int = 0) -> None:
+        """items: [(grid, level, h)] -- refresh h ghost rows on both sides of each level."""
+        if not items:
+            return
+        descs = (self.shim.HaloDesc * len(items))()
+        for d, (grid, lv, h) in zip(descs, items):
+            row = grid.stride0 * grid.itemsize
+            n0 = grid.shape[0]
+            d.bytes = h * row
+            d.lo_rank, d.hi_rank = self.topo.lo_rank, self.topo.hi_rank
+            d.send_lo = lv.dev                     # my first h rows -> rank-1's upper ghost
+            d.recv_lo = lv.dev - h * row           # my lower ghost   <- rank-1's last h rows
+            d.send_hi = lv.dev + (n0 - h) * row    # my last h rows   -> rank+1's lower ghost
+            d.recv_hi = lv.dev + n0 * row          # my upper ghost   <- rank+1's first h rows
+        self.shim.check(self.shim.lib().xgb_halo_exchange(descs, len(items), stream))
+        for _, lv, _ in items:
+            lv.halo_ok = True
+
+
+def transport():
+    global _transport
+    if _transport is None:
+        _transport = NcclTransport(topology())
+    return _transport

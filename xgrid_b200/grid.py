@@ -41,13 +41,14 @@ def parse_numpy_dtype(t: Value):
 
 class _Level:
     """One time level: device allocation + optional host mirror."""
-    __slots__ = ("dev", "host", "where", "raw")
+    __slots__ = ("dev", "host", "where", "raw", "halo_ok")
 
     def __init__(self, host=None) -> None:
         self.dev = 0            # device pointer of the first *real* element (0 = not allocated)
         self.host = host        # np.ndarray or None (an all-zero level never touched by the host)
         self.where = "host" if host is not None else "zero"
         self.raw = 0            # base of the padded device allocation
+        self.halo_ok = False    # ghost rows hold the neighbours' current rows (sharded grids)
 
 
 class Grid:
@@ -59,6 +60,19 @@ class Grid:
         if isinstance(shape, int):
             shape = (shape,)
         self.element = elem
+        self.global_shape = tuple(int(s) for s in shape)
+        self.row_range = (0, self.global_shape[0])
+        self.sharded = False
+        from .config import _config
+        if _config is not None and _config.distributed:
+            # slab decomposition along axis 0: this process holds rows [lo, hi) (xgrid_b200/dist.py);
+            # .now / .boundary / [] address the local slab
+            from . import dist
+            topo = dist.topology()
+            if topo.sharded:
+                self.row_range = dist.slab_range(self.global_shape[0], topo.rank, topo.world)
+                self.sharded = True
+        shape = (self.row_range[1] - self.row_range[0],) + self.global_shape[1:]
         self.shape = tuple(int(s) for s in shape)
         self.numpy_dtype = parse_numpy_dtype(elem)
         self.typing = GridT(elem, len(self.shape))
@@ -76,6 +90,7 @@ class Grid:
         self._mask_any = False
         self._lists: dict = {}          # mask value -> (device ptr, count)
         self._mask_version = 0
+        self._mask_hist = None
         self._ghost = 1                 # zero rows on both sides of axis 0
         self._allocs: list[int] = []    # raw device allocations to free
         self._rt = None
@@ -144,9 +159,11 @@ class Grid:
         return self._rt
 
     def _layout(self):
-        lead = (SLACK + self._ghost * self.stride0) * self.itemsize
+        # ghost rows + room for the tiled variant's halo'd bulk copies at the array ends
+        extra = SLACK + (2 * self.shape[-1] + 2048 if self.dimension > 1 else 0)
+        lead = (extra + self._ghost * self.stride0) * self.itemsize
         lead = (lead + ALIGN - 1) // ALIGN * ALIGN
-        tail = (SLACK + self._ghost * self.stride0) * self.itemsize
+        tail = (extra + self._ghost * self.stride0) * self.itemsize
         return lead, lead + self.size * self.itemsize + tail
 
     def _alloc_level(self, lv: _Level) -> None:
@@ -192,6 +209,7 @@ class Grid:
         elif lv.where == "zero":
             self._runtime().memset(lv.dev, 0, self.size * self.itemsize)
         lv.where = "device"
+        lv.halo_ok = False
 
     def _ensure_ghost(self, rows: int) -> None:
         if rows <= self._ghost:
@@ -228,6 +246,21 @@ class Grid:
         self._ring[0], self._scratch = self._scratch, self._ring[0]
         self._ring[0].where = "device"
 
+    def _arrangement(self) -> tuple:
+        """(device pointers of the ring in order, scratch pointer): the buffer state a
+        recorded CUDA graph was captured against / leaves behind."""
+        return (tuple(lv.dev for lv in self._ring), self._scratch.dev if self._scratch is not None else 0)
+
+    def _restore_arrangement(self, arrangement: tuple) -> None:
+        ring, scratch = arrangement
+        pool = {lv.dev: lv for lv in self._ring}
+        if self._scratch is not None:
+            pool[self._scratch.dev] = self._scratch
+        self._ring = [pool[d] for d in ring]
+        self._scratch = pool[scratch] if scratch else None
+        for lv in self._ring:
+            lv.where = "device"
+
     # ------------------------------------------------------------------ mask compilation
     def _upload_mask(self) -> None:
         self._mask_touched = False
@@ -240,6 +273,7 @@ class Grid:
                 rt.free(ptr)
         self._lists = {}
         self._mask_snapshot = b.copy()
+        self._mask_hist = None
         self._mask_version += 1
         flat = b.reshape(-1)
         self._mask_any = bool(flat.any())
@@ -261,9 +295,12 @@ class Grid:
         rt.sync()
 
     def _mask_count(self, k: int) -> int:
-        if self._mask_snapshot is None:
+        """Number of points whose boundary value is k (histogram cached per mask upload)."""
+        if self._mask_snapshot is None or not self._mask_any:
             return self.size if k == 0 else 0
-        return int(np.count_nonzero(self._mask_snapshot == k))
+        if self._mask_hist is None:
+            self._mask_hist = np.bincount(self._mask_snapshot.reshape(-1), minlength=256)
+        return int(self._mask_hist[k]) if 0 <= k < len(self._mask_hist) else 0
 
     def _index_list(self, k: int):
         """Device array of linear indices where boundary == k (cached per mask)."""

@@ -24,6 +24,11 @@ from . import ir
 
 VARIANT_DENSE = "dense"
 VARIANT_SPARSE = "sparse"
+VARIANT_MARCH = "march"
+VARIANT_TILED = "tiled"
+MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
+import os as _os
+MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "2"))   # rows loaded ahead of use per chain
 
 
 @dataclass
@@ -37,6 +42,7 @@ class Slot:
     elem: Value
     read: bool = False
     written: bool = False
+    halo0: int = 0          # max |axis-0 offset| this slot is read at (rows a slab must import)
 
     @property
     def field(self) -> str:
@@ -60,6 +66,8 @@ class Group:
     vwidths: tuple = (1,)
     halo0: int = 0                                # max |axis-0 offset| over all loads
     halo_last: int = 0
+    march: bool = False                           # has axis-0 marching variants
+    tiled: dict | None = None                     # geometry of the async shared-memory pipeline variant
 
     def slot(self, grid: str, level) -> Slot:
         for s in self.slots:
@@ -254,7 +262,9 @@ def analyse_group(g: Group, scope: dict) -> None:
             # unwritten points carry the old value through the double buffer
             slot(sw.grid.name, 0, sw.grid.type.element).read = True
         for ld in sw.loads:
-            slot(ld.variable.name, ld.level, ld.variable.type.element).read = True
+            sl = slot(ld.variable.name, ld.level, ld.variable.type.element)
+            sl.read = True
+            sl.halo0 = max(sl.halo0, abs(ld.space_offset[0]))
             g.halo0 = max(g.halo0, abs(ld.space_offset[0]) if g.ndim > 1 else 0)
             g.halo_last = max(g.halo_last, abs(ld.space_offset[-1]))
         for e in ir.walk_expr(a.value):
@@ -304,6 +314,7 @@ def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims:
         add("const uint8_t* __restrict__", f"f_{m}", ctypes.c_void_p)
     add("const int64_t* __restrict__", "list", ctypes.c_void_p)
     add("int64_t", "count", ctypes.c_int64)
+    add("int64_t", "chunk0", ctypes.c_int64)     # axis-0 points per CTA in the marching variant
     add("int64_t", "rows", ctypes.c_int64)
     add("int64_t", "cols", ctypes.c_int64)
     for a in range(g.ndim):
@@ -347,7 +358,16 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
         if module.overstep == "none":
             for v in g.vwidths:
                 module.kernels.append(_emit_windowed(g, module, v, VARIANT_DENSE))
-            module.kernels.append(_emit_windowed(g, module, 1, VARIANT_SPARSE))
+            if g.sparse:
+                module.kernels.append(_emit_windowed(g, module, 1, VARIANT_SPARSE))
+            g.march = march_supported(g)
+            if g.march:
+                for v in g.vwidths:
+                    if v > 1:
+                        module.kernels.append(_emit_march(g, module, v, MARCH_ROWS[g.ndim]))
+                g.tiled = tiled_config(g)
+                if g.tiled is not None:
+                    module.kernels.append(_emit_tiled(g, module, g.tiled))
         else:
             module.kernels.append(_emit_general(g, module, VARIANT_DENSE))
             module.kernels.append(_emit_general(g, module, VARIANT_SPARSE))
@@ -478,5 +498,328 @@ def _emit_general(g: Group, module: ModuleBuilder, variant: str) -> str:
     for s in g.slots:
         if s.written:
             L.append(f"    xgb::st_pred<{module.ctype(s.elem)}, V>(p.{s.field} + base, o_{s.field}, wr_{s.field});")
+    L.append("}")
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------- marching variant
+def march_supported(g: Group) -> bool:
+    """Axis-0 marching needs 2-D / 3-D number grids and no slot that is both read
+    and written by the group (in-place boundary statements stay on the direct path)."""
+    if g.ndim not in (2, 3) or g.sparse:
+        return False
+    for s in g.slots:
+        if s.read and s.written:
+            return False
+        if isinstance(s.elem, (Structure, Boolean)):
+            return False
+    return True
+
+
+def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
+    """Each thread owns V contiguous columns (and one axis-1 index in 3-D) and
+    marches R points along axis 0.  Taps that differ only in their axis-0 offset
+    form a *chain* whose bodies stay in registers and rotate, so every input
+    element is loaded once per thread; contiguous-axis neighbours come from the
+    adjacent lanes by shuffle (xgb::window_from_body)."""
+    nd = g.ndim
+    chains: dict = {}      # (slot index, mid offsets) -> {"dmin","dmax","fringe": {d0: [lo, hi]}}
+
+    def need(slot: Slot, off: tuple) -> None:
+        key = (slot.index, tuple(off[1:-1]))
+        ch = chains.setdefault(key, {"dmin": off[0], "dmax": off[0], "fringe": {}})
+        ch["dmin"], ch["dmax"] = min(ch["dmin"], off[0]), max(ch["dmax"], off[0])
+        lo, hi = ch["fringe"].get(off[0], (0, 0))
+        ch["fringe"][off[0]] = (min(lo, off[-1]), max(hi, off[-1]))
+
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            need(g.slot(ld.variable.name, ld.level), ld.space_offset)
+        if g.implicit:
+            need(g.slot(a.sweep.grid.name, 0), (0,) * nd)
+    for n, ch in enumerate(chains.values()):
+        ch["id"] = n
+        for lo, hi in ch["fringe"].values():
+            if -lo > V or hi > V:
+                raise CodegenError("contiguous-axis offset wider than the vector body")
+
+    def reg(ch, d0) -> str:
+        return f"c{ch['id']}_{d0 - ch['dmin']}"
+
+    def tap(e: ir.Stencil) -> str:
+        slot = g.slot(e.variable.name, e.level)
+        ch = chains[(slot.index, tuple(e.space_offset[1:-1]))]
+        d0, dk = e.space_offset[0], e.space_offset[-1]
+        lo, hi = ch["fringe"][d0]
+        if (lo, hi) == (0, 0):
+            return f"{reg(ch, d0)}[v]"
+        return f"w{ch['id']}_{d0 - ch['dmin']}[v + {dk - lo}]"
+
+    def mid_text(mid: tuple) -> str:
+        terms = []
+        for a, d in enumerate(mid, start=1):
+            if d:
+                stride = " * ".join(f"p.n{b}" for b in range(a + 1, nd))
+                terms.append(f"({d}LL) * {stride}")
+        return " + ".join(terms) if terms else "0"
+
+    name = kernel_name(g, VARIANT_MARCH, V)
+    L = [f'extern "C" __global__ void __launch_bounds__(256) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int V = {V}, R = {R};")
+    L.append("    const int lane = threadIdx.x & 31;")
+    L.append("    const int64_t col_raw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;")
+    L.append("    const bool act_c = col_raw < p.cols;")
+    L.append("    const int64_t col = act_c ? col_raw : (p.cols - V);")
+    L.append("    const bool edge_l = (lane == 0);")
+    L.append("    const bool edge_r = (lane == 31) || (col_raw + V >= p.cols);")
+    if nd == 3:
+        L.append("    const int64_t j_raw = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;")
+        L.append("    const bool act = act_c && (j_raw < p.n1);")
+        L.append("    const int64_t j = j_raw < p.n1 ? j_raw : (p.n1 - 1);")
+        L.append("    const int64_t i0 = (int64_t)blockIdx.z * p.chunk0;")
+        L.append("    const int64_t S0 = p.n1 * p.n2;")
+        L.append("    int64_t base = i0 * S0 + j * p.cols + col;")
+    else:
+        L.append("    const bool act = act_c;")
+        L.append("    const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
+        L.append("    const int64_t S0 = p.cols;")
+        L.append("    int64_t base = i0 * S0 + col;")
+    L.append("    if (i0 >= p.n0) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.n0) ? (i0 + p.chunk0) : p.n0;")
+    # chain registers + prologue (all but the leading row of every chain)
+    PF = MARCH_PREFETCH
+    for ch in chains.values():
+        ch["top"] = ch["dmax"] + PF          # furthest row held in registers (prefetched, not yet used)
+    # rows past the slab's last ghost row must not be touched: clamp the prefetch distance
+    L.append("    #define XGB_ROW(d, dmax) ((ib + r + (d) <= p.n0 - 1 + (dmax)) ? (int64_t)(d) : (p.n0 - 1 + (dmax) - (ib + r)))")
+    for key, ch in chains.items():
+        slot = g.slots[key[0]]
+        t = module.ctype(slot.elem)
+        for d0 in range(ch["dmin"], ch["top"] + 1):
+            L.append(f"    {t} {reg(ch, d0)}[V];")
+    L.append("    { const int64_t ib = i0; const int r = 0;")
+    for key, ch in chains.items():
+        slot = g.slots[key[0]]
+        t = module.ctype(slot.elem)
+        for d0 in range(ch["dmin"], ch["top"]):
+            L.append(f"    xgb::ld_vec<{t}, V>(p.{slot.field} + (base + XGB_ROW({d0}, {ch['dmax']}) * S0 + {mid_text(key[1])}), {reg(ch, d0)});")
+    L.append("    }")
+    L.append("    for (int64_t ib = i0; ib < iend; ib += R) {")
+    L.append("#pragma unroll")
+    L.append("    for (int r = 0; r < R; ++r) {")
+    L.append("        if (ib + r >= iend) break;")
+    for key, ch in chains.items():
+        slot = g.slots[key[0]]
+        t = module.ctype(slot.elem)
+        d0 = ch["top"]
+        L.append(f"        xgb::ld_vec<{t}, V>(p.{slot.field} + (base + XGB_ROW({d0}, {ch['dmax']}) * S0 + {mid_text(key[1])}), {reg(ch, d0)});")
+    for m in g.masks:
+        L.append(f"        int m_{m}[V]; xgb::ld_mask<V>(p.m_{m}, p.f_{m}, base, m_{m});")
+    for key, ch in chains.items():
+        slot = g.slots[key[0]]
+        t = module.ctype(slot.elem)
+        for d0, (lo, hi) in ch["fringe"].items():
+            if (lo, hi) != (0, 0):
+                wn = f"w{ch['id']}_{d0 - ch['dmin']}"
+                L.append(f"        {t} {wn}[V + {hi - lo}]; xgb::window_from_body<{t}, V, {lo}, {hi}>("
+                         f"p.{slot.field} + (base + ({d0}LL) * S0 + {mid_text(key[1])}), {reg(ch, d0)}, edge_l, edge_r, {wn});")
+    for s in g.slots:
+        if s.written:
+            L.append(f"        {module.ctype(s.elem)} o_{s.field}[V]; unsigned wr_{s.field} = 0u;")
+    L.append("#pragma unroll")
+    L.append("        for (int v = 0; v < V; ++v) {")
+    body: list = []
+    _emit_statements(g, module, tap, body, "v")
+    L.extend("    " + b for b in body)
+    L.append("        }")
+    for s in g.slots:
+        if s.written:
+            L.append(f"        if (act) xgb::st_pred<{module.ctype(s.elem)}, V>(p.{s.field} + base, o_{s.field}, wr_{s.field});")
+    for ch in chains.values():
+        for d0 in range(ch["dmin"], ch["top"]):
+            L.append(f"#pragma unroll\n        for (int v = 0; v < V; ++v) {reg(ch, d0)}[v] = {reg(ch, d0 + 1)}[v];")
+    L.append("        base += S0;")
+    L.append("    }")
+    L.append("    }")
+    L.append("    #undef XGB_ROW")
+    L.append("}")
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------- tiled (async pipeline) variant
+TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", str(56 * 1024)))
+TILED_TJ = int(_os.environ.get("XGB_TJ", "8"))
+
+
+def tiled_config(g: Group):
+    """Geometry of the bulk-copy pipeline variant, or None when the group does not
+    qualify (needs 2-D/3-D, one element width across all slots, halo that fits)."""
+    widths = {s.elem.width_bytes for s in g.slots}
+    if len(widths) != 1:
+        return None
+    esize = widths.pop()
+    if esize not in (4, 8):
+        return None
+    V = 16 // esize
+    NSV = 2
+    dmin = dmax = hj = hk = 0
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            off = ld.space_offset
+            dmin, dmax = min(dmin, off[0]), max(dmax, off[0])
+            if g.ndim == 3:
+                hj = max(hj, abs(off[1]))
+            hk = max(hk, abs(off[-1]))
+    hk = -(-hk // V) * V                       # keep shared rows 16-byte aligned
+    if g.ndim == 2:
+        ncw, tj, wx = 8, 1, 8                  # 8 consumer warps side by side
+    else:
+        tj, wx = TILED_TJ, 1                   # one warp per j-row
+        ncw = tj * wx
+    W = wx * 32 * V * NSV
+    wp, rp = W + 2 * hk, tj + 2 * hj
+    nread = sum(1 for s in g.slots if s.read)
+    if nread == 0:
+        return None
+    stage_bytes = nread * rp * wp * esize
+    ns = min(8, max((dmax - dmin) + 3, (TILED_SMEM_BUDGET - 256) // stage_bytes))
+    if 256 + ns * stage_bytes > 200 * 1024:
+        return None
+    return {"V": V, "NSV": NSV, "NCW": ncw, "TJ": tj, "WX": wx, "W": W, "HJ": hj, "HK": hk, "WP": wp,
+            "RP": rp, "NS": ns, "DMIN": dmin, "DMAX": dmax, "NREAD": nread, "ESIZE": esize,
+            "smem": 256 + ns * stage_bytes, "threads": (ncw + 1) * 32}
+
+
+def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
+    nd = g.ndim
+    V, NSV = c["V"], c["NSV"]
+    read_slots = [s for s in g.slots if s.read]
+    ridx = {s.index: n for n, s in enumerate(read_slots)}
+    T = module.ctype(read_slots[0].elem)
+
+    # windows per (read slot, di, dj): [lo, hi] over dk
+    windows: dict = {}
+
+    def need(slot: Slot, off: tuple) -> None:
+        key = (slot.index, off[0], off[1] if nd == 3 else 0)
+        lo, hi = windows.get(key, (0, 0))
+        windows[key] = (min(lo, off[-1]), max(hi, off[-1]))
+
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            need(g.slot(ld.variable.name, ld.level), ld.space_offset)
+        if g.implicit:
+            need(g.slot(a.sweep.grid.name, 0), (0,) * nd)
+    wnames = {key: f"w{n}" for n, key in enumerate(windows)}
+
+    def tap(e: ir.Stencil) -> str:
+        slot = g.slot(e.variable.name, e.level)
+        key = (slot.index, e.space_offset[0], e.space_offset[1] if nd == 3 else 0)
+        lo, _ = windows[key]
+        return f"{wnames[key]}[v + {e.space_offset[-1] - lo}]"
+
+    name = kernel_name(g, VARIANT_TILED, V)
+    L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int V = {V}, NSV = {NSV}, NCW = {c['NCW']}, TJ = {c['TJ']}, WX = {c['WX']}, W = {c['W']};")
+    L.append(f"    constexpr int HJ = {c['HJ']}, HK = {c['HK']}, WP = {c['WP']}, RP = {c['RP']}, NS = {c['NS']};")
+    L.append(f"    constexpr int DMIN = {c['DMIN']}, DMAX = {c['DMAX']}, DSPAN = DMAX - DMIN, NREAD = {c['NREAD']};")
+    L.append(f"    typedef {T} T;")
+    L.append("    constexpr int STAGE = RP * WP;                       // elements per (slot, plane)")
+    L.append("    extern __shared__ __align__(128) unsigned char xgb_smem[];")
+    L.append("    uint64_t *full = reinterpret_cast<uint64_t *>(xgb_smem);")
+    L.append("    uint64_t *empty = full + NS;")
+    L.append("    T *stages = reinterpret_cast<T *>(xgb_smem + 256);   // [NS][NREAD][RP][WP]")
+    L.append("    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+    L.append("    const int64_t c0 = (int64_t)blockIdx.x * W;")
+    if nd == 3:
+        L.append("    const int64_t j0 = (int64_t)blockIdx.y * TJ;")
+        L.append("    const int64_t i0 = (int64_t)blockIdx.z * p.chunk0;")
+        L.append("    const int64_t S0 = p.n1 * p.n2;")
+    else:
+        L.append("    const int64_t j0 = 0;")
+        L.append("    const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
+        L.append("    const int64_t S0 = p.cols;")
+    L.append("    if (i0 >= p.n0) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.n0) ? (i0 + p.chunk0) : p.n0;")
+    L.append("    const int planes = (int)(iend - i0) + DSPAN;          // input planes this CTA streams")
+    L.append("    if (threadIdx.x == 0) {")
+    L.append("        for (int s = 0; s < NS; ++s) { xgb::pipe::mbar_init(&full[s], 1); xgb::pipe::mbar_init(&empty[s], NCW); }")
+    L.append("        xgb::pipe::fence_barrier_init();")
+    L.append("    }")
+    L.append("    __syncthreads();")
+    # ---------------- producer warp
+    L.append("    if (warp == NCW) {")
+    L.append("        const T *src[NREAD] = {" + ", ".join(f"p.{s.field}" for s in read_slots) + "};")
+    L.append("        for (int t = 0; t < planes; ++t) {")
+    L.append("            const int s = t % NS;")
+    L.append("            if (t >= NS) xgb::pipe::mbar_wait(&empty[s], ((t / NS) - 1) & 1);")
+    L.append("            if (lane == 0) xgb::pipe::mbar_expect_tx(&full[s], (uint32_t)(NREAD * RP * WP * sizeof(T)));")
+    L.append("            __syncwarp();")
+    L.append("            const int64_t plane = i0 + DMIN + t;")
+    L.append("            for (int q = lane; q < NREAD * RP; q += 32) {")
+    L.append("                const int r = q / RP, jj = q % RP;")
+    if nd == 3:
+        L.append("                int64_t j = j0 - HJ + jj;")
+        L.append("                if (j > p.n1 - 1 + HJ) j = p.n1 - 1 + HJ;")
+        L.append("                const T *g = src[r] + (plane * S0 + j * p.n2 + (c0 - HK));")
+    else:
+        L.append("                const T *g = src[r] + (plane * S0 + (c0 - HK));")
+    L.append("                xgb::pipe::bulk_g2s(stages + ((int64_t)(s * NREAD + r) * RP + jj) * WP, g, (uint32_t)(WP * sizeof(T)), &full[s]);")
+    L.append("            }")
+    L.append("        }")
+    L.append("        return;")
+    L.append("    }")
+    # ---------------- consumer warps
+    L.append("    const int ty = warp / WX, wx = warp % WX;")
+    L.append("    const int64_t j = j0 + ty;")
+    L.append("    int kk[NSV]; bool act[NSV]; int64_t base[NSV];")
+    L.append("#pragma unroll")
+    L.append("    for (int sv = 0; sv < NSV; ++sv) {")
+    L.append("        kk[sv] = (wx * NSV + sv) * (32 * V) + lane * V;")
+    L.append("        const int64_t col = c0 + kk[sv];")
+    L.append("        act[sv] = (col < p.cols)" + (" && (j < p.n1);" if nd == 3 else ";"))
+    L.append("        base[sv] = act[sv] ? (i0 * S0 + " + ("j * p.n2 + " if nd == 3 else "") + "col) : (i0 * S0);")
+    L.append("    }")
+    for m in g.masks:
+        L.append(f"    int fl_{m}[NSV];")
+        L.append(f"#pragma unroll\n    for (int sv = 0; sv < NSV; ++sv) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv]);")
+    L.append("    const T *srow = stages + (int64_t)(ty + HJ) * WP + HK;   // this warp's row inside a plane")
+    L.append("    int tn = 0;                                           // newest plane waited for")
+    L.append("    for (; tn < DSPAN; ++tn) xgb::pipe::mbar_wait(&full[tn % NS], (tn / NS) & 1);")
+    L.append("    int ps = 0;                                           // stage of plane o + DMIN")
+    L.append("    for (int64_t o = i0; o < iend; ++o, ++tn) {")
+    for m in g.masks:
+        L.append(f"        int fc_{m}[NSV];")
+        L.append(f"#pragma unroll\n        for (int sv = 0; sv < NSV; ++sv) {{ fc_{m}[sv] = fl_{m}[sv]; "
+                 f"if (o + 1 < iend) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv] + S0); }}")
+    L.append("        xgb::pipe::mbar_wait(&full[tn % NS], (tn / NS) & 1);")
+    L.append("#pragma unroll")
+    L.append("        for (int sv = 0; sv < NSV; ++sv) {")
+    for m in g.masks:
+        L.append(f"            int m_{m}[V];")
+        L.append(f"            if (act[sv]) xgb::ld_mask_flagged<V>(p.m_{m}, fc_{m}[sv], base[sv], m_{m}); else {{ for (int v = 0; v < V; ++v) m_{m}[v] = -1; }}")
+    for key, (lo, hi) in windows.items():
+        si, di, dj = key
+        L.append(f"            T {wnames[key]}[V + {hi - lo}];")
+        L.append(f"            {{ int q = ps + ({di} - DMIN); if (q >= NS) q -= NS;")
+        L.append(f"              xgb::lds_window<T, V, {lo}, {hi}>(srow + ((int64_t)(q * NREAD + {ridx[si]}) * RP + ({dj})) * WP + kk[sv], {wnames[key]}); }}")
+    for s_ in g.slots:
+        if s_.written:
+            L.append(f"            {module.ctype(s_.elem)} o_{s_.field}[V]; unsigned wr_{s_.field} = 0u;")
+    L.append("#pragma unroll")
+    L.append("            for (int v = 0; v < V; ++v) {")
+    body: list = []
+    _emit_statements(g, module, tap, body, "v")
+    L.extend("        " + b for b in body)
+    L.append("            }")
+    for s_ in g.slots:
+        if s_.written:
+            L.append(f"            if (act[sv]) xgb::st_pred<{module.ctype(s_.elem)}, V>(p.{s_.field} + base[sv], o_{s_.field}, wr_{s_.field});")
+    L.append("            base[sv] += S0;")
+    L.append("        }")
+    L.append("        __syncwarp();")
+    L.append("        if (lane == 0) xgb::pipe::mbar_arrive(&empty[ps]);       // plane o + DMIN is dead")
+    L.append("        ps = (ps + 1 == NS) ? 0 : ps + 1;")
+    L.append("    }")
     L.append("}")
     return "\n".join(L) + "\n"

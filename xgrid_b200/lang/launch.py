@@ -8,6 +8,7 @@ cached instead of rebuilt every call.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import astuple
 
 import numpy as np
@@ -39,13 +40,74 @@ def dense_geometry(rows: int, cols: int, V: int):
     return (gx, gy, gz), (tx, ty, 1)
 
 
+# launch-time tunables (overridable from the environment for on-GPU experiments)
+TUNE = {
+    "vec_bytes": int(os.environ.get("XGB_VEC_BYTES", "32")),
+    "march": os.environ.get("XGB_MARCH", "1") != "0",
+    "tiled": os.environ.get("XGB_TILED", "1") != "0",
+    "tx": int(os.environ.get("XGB_TX", "0")),
+    "ty": int(os.environ.get("XGB_TY", "0")),
+    "chunk0": int(os.environ.get("XGB_CHUNK0", "0")),
+    "min_ctas": int(os.environ.get("XGB_MIN_CTAS", "8192")),
+}
+
+
+def march_geometry(shape, V: int, R: int):
+    """2-D: blockDim=(TX,1), grid=(col blocks, axis-0 chunks).  3-D: blockDim=(TX,TY)
+    over (k, j) so that j+-1 taps hit L1, grid.z walks the axis-0 chunks.  A CTA
+    marches `chunk0` points along axis 0; its two halo planes are the only re-read
+    traffic, so chunks are made as long as possible while leaving >= MIN_CTAS CTAs."""
+    cols = shape[-1]
+    vec_cols = (cols + V - 1) // V
+    if len(shape) == 2:
+        tx = TUNE["tx"] or min(256, max(32, _pow2ceil(vec_cols)))
+        ty, gy_mid = 1, 1
+    else:
+        tx = TUNE["tx"] or min(128, max(32, _pow2ceil(vec_cols)))
+        ty = TUNE["ty"] or max(1, min(256 // tx, _pow2ceil(shape[1])))
+        gy_mid = (shape[1] + ty - 1) // ty
+    gx = (vec_cols + tx - 1) // tx
+    want_chunks = max(1, -(-TUNE["min_ctas"] // (gx * gy_mid)))
+    chunk0 = max(R, -(-shape[0] // want_chunks))
+    chunk0 = -(-chunk0 // R) * R
+    if TUNE["chunk0"]:
+        chunk0 = TUNE["chunk0"]
+    chunks = (shape[0] + chunk0 - 1) // chunk0
+    if len(shape) == 2:
+        gy = min(chunks, 65535)
+        gz = (chunks + gy - 1) // gy
+        return (gx, gy, gz), (tx, 1, 1), chunk0
+    return (gx, gy_mid, chunks), (tx, ty, 1), chunk0
+
+
+def tiled_geometry(shape, t: dict):
+    """grid = (column tiles, j tiles | axis-0 chunks, axis-0 chunks); one CTA streams
+    `chunk0` planes through its shared-memory ring."""
+    gx = (shape[-1] + t["W"] - 1) // t["W"]
+    gy_mid = 1 if len(shape) == 2 else (shape[1] + t["TJ"] - 1) // t["TJ"]
+    want_chunks = max(1, -(-TUNE["min_ctas"] // (gx * gy_mid)))
+    chunk0 = TUNE["chunk0"] or max(16, -(-shape[0] // want_chunks))
+    chunks = (shape[0] + chunk0 - 1) // chunk0
+    block = (t["threads"], 1, 1)
+    if len(shape) == 2:
+        gy = min(chunks, 65535)
+        return (gx, gy, (chunks + gy - 1) // gy), block, chunk0
+    return (gx, gy_mid, chunks), block, chunk0
+
+
 class Launcher:
     def __init__(self, program, grids: dict) -> None:
-        from ..runtime.shim import Runtime
         self.program = program
         self.grids = grids
-        self.rt = Runtime.get()
+        self._rt = None
         self.launches = 0
+
+    @property
+    def rt(self):
+        if self._rt is None:
+            from ..runtime.shim import Runtime
+            self._rt = Runtime.get()
+        return self._rt
 
     def _scalar_value(self, t, raw):
         if isinstance(t, Pointer):
@@ -65,6 +127,8 @@ class Launcher:
                                 f"runs on {lead.shape}; all grids of one stencil statement must agree")
             lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
             setattr(P, s.field, lv.dev)
+        if lead.sharded:
+            self._refresh_halos(g)
         for m in g.masks:
             grid = self.grids[m]
             setattr(P, f"m_{m}", grid._mask_dev if grid._mask_any else None)
@@ -84,7 +148,7 @@ class Launcher:
 
         if lead.size == 0:
             return
-        variant, V = cudagen.VARIANT_DENSE, 1
+        variant, V, smem = cudagen.VARIANT_DENSE, 1, 0
         if g.sparse:
             k = g.stmts[0].sweep.mask
             count = lead._mask_count(k)
@@ -95,19 +159,49 @@ class Launcher:
                 ptr, count = lead._index_list(k)
                 P.list, P.count = ptr, count
         if variant == cudagen.VARIANT_DENSE:
+            vmax = max(1, TUNE["vec_bytes"] // max(s.elem.width_bytes if hasattr(s.elem, "width_bytes") else 16
+                                                   for s in g.slots))
             for cand in sorted(g.vwidths, reverse=True):
-                if cols % cand == 0:
+                if cols % cand == 0 and cand <= vmax:
                     V = cand
                     break
-            grid_dim, block_dim = dense_geometry(rows, cols, V)
+            t = g.tiled
+            if (t is not None and TUNE["tiled"] and cols % t["V"] == 0 and cols >= t["W"] and shape[0] >= 16
+                    and (g.ndim == 2 or shape[1] >= t["TJ"])):
+                variant, V = cudagen.VARIANT_TILED, t["V"]
+                grid_dim, block_dim, P.chunk0 = tiled_geometry(shape, t)
+                smem = t["smem"]
+            elif g.march and V > 1 and TUNE["march"] and shape[0] >= 4:
+                variant = cudagen.VARIANT_MARCH
+                grid_dim, block_dim, P.chunk0 = march_geometry(shape, V, cudagen.MARCH_ROWS[g.ndim])
+            else:
+                grid_dim, block_dim = dense_geometry(rows, cols, V)
         else:
             block_dim = (128, 1, 1)
             grid_dim = ((P.count + 127) // 128, 1, 1)
-        fn = self.program.function(cudagen.kernel_name(g, variant, V))
-        self.rt.launch(fn, grid_dim, block_dim, P)
+        fn = self.program.function(cudagen.kernel_name(g, variant, V), smem)
+        self.rt.launch(fn, grid_dim, block_dim, P, smem=smem)
         self.launches += 1
+        for s in g.slots:
+            if s.written:
+                grid = self.grids[s.grid]
+                (grid._scratch if s.level == "scratch" else grid._ring[s.level]).halo_ok = False
         if g.implicit:
             self.grids[g.stmts[0].sweep.grid.name]._swap_scratch()
+
+    def _refresh_halos(self, g: cudagen.Group) -> None:
+        """Sharded grids: import the neighbours' rows into the ghost rows of every level
+        this group reads at a non-zero axis-0 offset and that changed since its last exchange."""
+        from .. import dist
+        reads = []
+        for s in g.slots:
+            if s.read and s.halo0 > 0:
+                grid = self.grids[s.grid]
+                lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
+                reads.append((grid, lv, s.halo0))
+        stale = dist.HaloPlan.stale(reads)
+        if stale:
+            dist.transport().exchange(stale)
 
     def finish(self) -> None:
         pass
