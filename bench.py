@@ -206,12 +206,23 @@ def run_ours(args, rank: int, world: int):
                distributed=world > 1)
     kern = W.make_kernels()[spec["kernel"]]
     rt = Runtime.get()
-    inputs, scalars = build_inputs(name, shape, seed=rank)
+    if world > 1:
+        # weak scaling: every rank owns a `shape` slab of the (world*shape[0], ...) global grid
+        if name != "heat3d":
+            raise SystemExit("multi-GPU bench is defined for the slab-sharded 3-D 7-point sweep (heat3d)")
+        gshape = (shape[0] * world,) + tuple(shape[1:])
+        lo, hi = rank * shape[0], (rank + 1) * shape[0]
+        rng = np.random.default_rng(rank)
+        inputs, scalars = [(rng.random(shape), W.shell_mask_slab(gshape, lo, hi))], (0.1,)
+    else:
+        gshape = shape
+        inputs, scalars = build_inputs(name, shape, seed=rank)
 
     def fresh_grids():
         out = []
         for ic, mask in inputs:
-            g = xgrid.Grid(shape, float)
+            g = xgrid.Grid(gshape, float)
+            assert g.shape == tuple(shape), (g.shape, shape)
             g.now[...] = ic
             g.boundary[...] = mask
             out.append(g)
@@ -219,8 +230,11 @@ def run_ours(args, rank: int, world: int):
 
     def barrier():
         if world > 1:
+            import torch
             import torch.distributed as dist
+            rt.device_sync()
             dist.barrier()
+            torch.cuda.synchronize()
 
     points = float(np.prod(shape))
     # ---- device-resident throughput (`value`) ---------------------------------
@@ -292,7 +306,7 @@ def run_ours(args, rank: int, world: int):
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "xgrid_b200",
-        "config": {"workload": f"{name} {'x'.join(map(str, shape))} fp64" + (" per GPU" if world > 1 else ""),
+        "config": {"workload": f"{name} {'x'.join(map(str, shape))} fp64" + (" per GPU, slab-sharded on axis 0, NCCL halo exchange" if world > 1 else ""),
                    "kernel": spec["kernel"], "interior_statements_per_step": spec["stmts"],
                    "l2": "working set (2 levels) larger than the 126 MB L2" if points * 16 > 126e6 else "L2-resident (small grid)",
                    "validate_build": True},

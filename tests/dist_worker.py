@@ -1,0 +1,119 @@
+"""Worker for the 2-rank tests (launched by torch.distributed.run).
+
+    mode=cpu : gloo; exercises slab_range / Grid sharding / HaloPlan on the host and checks
+               a slab-decomposed oracle run (ghost rows exchanged over gloo) against the
+               single-domain oracle.
+    mode=gpu : nccl; the sharded CUDA path against the single-domain oracle, bit-exact.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import oracle
+from oracle import HostGrid
+import xgrid_b200 as xgrid
+from xgrid_b200 import dist as xdist
+from xgrid_b200 import workloads as W
+
+
+def oracle_global(shape, ic, mask, steps, a):
+    h = HostGrid(shape)
+    h.now[...] = ic
+    h.boundary[...] = mask
+    for _ in range(steps):
+        oracle.step_heat3d(h, a)
+    return h
+
+
+def exchange_host(h: HostGrid, level: int, topo, rows: int = 1):
+    """Ghost-row exchange of a HostGrid level over the default (gloo) group: the same
+    send/recv pattern NcclTransport.exchange issues (first rows down, last rows up)."""
+    arr = h._data[level]
+    n0 = arr.shape[0]
+    flat = arr.base                      # padded 1-D buffer; ghost rows sit right outside the view
+    stride0 = h.size // n0
+    start = h._pad
+    reqs = []
+    if topo.lo_rank >= 0:
+        send = torch.from_numpy(np.ascontiguousarray(arr[:rows]).reshape(-1))
+        recv = torch.empty(rows * stride0, dtype=torch.float64)
+        reqs += [dist.isend(send, topo.lo_rank), dist.irecv(recv, topo.lo_rank)]
+    if topo.hi_rank >= 0:
+        send2 = torch.from_numpy(np.ascontiguousarray(arr[n0 - rows:]).reshape(-1))
+        recv2 = torch.empty(rows * stride0, dtype=torch.float64)
+        reqs += [dist.isend(send2, topo.hi_rank), dist.irecv(recv2, topo.hi_rank)]
+    for r in reqs:
+        r.wait()
+    if topo.lo_rank >= 0:
+        flat[start - rows * stride0:start] = recv.numpy()
+    if topo.hi_rank >= 0:
+        flat[start + h.size:start + h.size + rows * stride0] = recv2.numpy()
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    gshape = (23, 12, 130) if mode == "cpu" else (40, 24, 256)
+    steps, a = 5, 0.1
+    rng = np.random.default_rng(7)
+    ic = rng.random(gshape)
+    mask = W.shell_mask(gshape)
+
+    if mode == "cpu":
+        dist.init_process_group("gloo")
+        xgrid.init(precision="double", distributed=True, cacheroot=os.environ.get("XG_CACHE", ".xgrid"))
+        topo = xdist.topology()
+        assert (topo.rank, topo.world) == (rank, world)
+        lo, hi = xdist.slab_range(gshape[0], rank, world)
+        g = xgrid.Grid(gshape, float)                  # product Grid: shards itself, host-only here
+        assert g.sharded and g.row_range == (lo, hi) and g.shape == (hi - lo,) + gshape[1:]
+        assert np.array_equal(W.shell_mask_slab(gshape, lo, hi), mask[lo:hi])
+        # HaloPlan: a stale level of a sharded grid read at axis-0 offset 1 must be exchanged once
+        lv = g._ring[0]
+        assert xdist.HaloPlan.stale([(g, lv, 1), (g, lv, 1), (g, lv, 0)]) == [(g, lv, 1)]
+        lv.halo_ok = True
+        assert xdist.HaloPlan.stale([(g, lv, 1)]) == []
+        # slab-decomposed oracle run with gloo ghost exchange == single-domain oracle
+        h = HostGrid((hi - lo,) + gshape[1:])
+        h.now[...] = ic[lo:hi]
+        h.boundary[...] = mask[lo:hi]
+        for _ in range(steps):
+            exchange_host(h, 0, topo)                  # the level the next step reads (becomes level 1)
+            oracle.step_heat3d(h, a)
+        ref = oracle_global(gshape, ic, mask, steps, a)
+        assert np.array_equal(h.now, ref.now[lo:hi]), "sharded oracle differs from single-domain oracle"
+        dist.barrier()
+        if rank == 0:
+            print("DIST_CPU_OK")
+    else:
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        xgrid.init(precision="double", distributed=True, device=local,
+                   cacheroot=os.environ.get("XG_CACHE", ".xgrid"))
+        k = W.make_kernels()
+        u = xgrid.Grid(gshape, float)
+        lo, hi = u.row_range
+        u.now[...] = ic[lo:hi]
+        u.boundary[...] = mask[lo:hi]
+        for _ in range(steps):
+            k["heat_3d"](u, a)
+        ref = oracle_global(gshape, ic, mask, steps, a)
+        ok = np.array_equal(u.now, ref.now[lo:hi]) and np.array_equal(u._data[1], ref._data[1][lo:hi])
+        t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("DIST_GPU_OK" if int(t.item()) == 1 else "DIST_GPU_MISMATCH")
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

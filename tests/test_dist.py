@@ -1,0 +1,51 @@
+"""Multi-rank path: partition / planning logic on CPU over gloo (world_size 2), and the
+sharded CUDA path over NCCL on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from xgrid_b200 import dist as xdist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_range_partitions_exactly():
+    for n0 in (1, 7, 8, 23, 256, 2048):
+        for world in (1, 2, 3, 4, 8):
+            spans = [xdist.slab_range(n0, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n0
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_topology_chain():
+    t = xdist.Topology(0, 4)
+    assert (t.lo_rank, t.hi_rank) == (-1, 1)
+    t = xdist.Topology(3, 4)
+    assert (t.lo_rank, t.hi_rank) == (2, -1)
+    assert not xdist.Topology(0, 1).sharded
+
+
+def _run(mode, nproc, tmp_path, port):
+    env = dict(os.environ, XG_CACHE=str(tmp_path / "xg"), OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_worker.py"), mode]
+    return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600, cwd=str(tmp_path))
+
+
+def test_two_ranks_gloo_cpu(tmp_path):
+    r = _run("cpu", 2, tmp_path, 29611)
+    assert "DIST_CPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_two_ranks_nccl_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _run("gpu", 2, tmp_path, 29612)
+    assert "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -100,13 +100,24 @@ class NcclTransport:
         self.rt = shim.Runtime.get()
         lib = shim.lib()
         nccl_path = ""
-        try:
-            import nvidia.nccl
-            cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
-            if os.path.exists(cand):
-                nccl_path = cand
-        except ImportError:
+        try:     # use the very libnccl torch already mapped into this process
+            with open("/proc/self/maps") as maps:
+                for line in maps:
+                    if "libnccl.so" in line:
+                        nccl_path = line.split()[-1]
+                        break
+        except OSError:
             pass
+        if not nccl_path:
+            try:
+                import nvidia.nccl
+                for base in list(getattr(nvidia.nccl, "__path__", [])):
+                    cand = os.path.join(base, "lib", "libnccl.so.2")
+                    if os.path.exists(cand):
+                        nccl_path = cand
+                        break
+            except ImportError:
+                pass
         shim.check(lib.xgb_nccl_load(nccl_path.encode()))
         store = dist.distributed_c10d._get_default_store()
         key = "xgrid_b200/nccl_id"

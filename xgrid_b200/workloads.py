@@ -183,6 +183,18 @@ def shell_mask(shape, value: int = 1) -> np.ndarray:
     return m
 
 
+def shell_mask_slab(global_shape, lo: int, hi: int, value: int = 1) -> np.ndarray:
+    """Rows [lo, hi) of shell_mask(global_shape) without materialising the global mask."""
+    local = (hi - lo,) + tuple(global_shape[1:])
+    m = np.full(local, value, np.int32)
+    inner = tuple(slice(1, -1) for _ in global_shape[1:])
+    a = max(lo, 1) - lo
+    b = min(hi, global_shape[0] - 1) - lo
+    if b > a:
+        m[(slice(a, b),) + inner] = 0
+    return m
+
+
 def cavity_masks(n0: int, n1: int):
     """examples/cavity.py:56-68 -> (mb, mp, mu, mv)"""
     mu = np.zeros((n0, n1), np.int32)
