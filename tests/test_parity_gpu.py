@@ -203,3 +203,31 @@ def test_host_write_between_calls(k64):
             h[7] = -1.0
     eq(u._data[0], h._data[0])
     eq(u._data[1], h._data[1])
+
+
+def test_division_is_ieee_exact_on_special_values(tmp_path):
+    """xgb::fdiv's zero-numerator shortcut must be bit-identical to IEEE division
+    (what the reference's SSE2 divsd computes), including signed zeros, inf, nan, subnormals."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def divide(r: f1, a: f1, b: f1) -> None:
+        r[0] = a[0] / b[0]
+
+    special = np.array([0.0, -0.0, 1.0, -1.0, 5e-324, -5e-324, 2.2250738585072014e-308, 1e308, -1e308,
+                        np.inf, -np.inf, np.nan, 3.0, 1e-310, 0.1])
+    rng = np.random.default_rng(11)
+    av = np.concatenate([np.repeat(special, len(special)), rng.standard_normal(4096)])
+    bv = np.concatenate([np.tile(special, len(special)), rng.standard_normal(4096)])
+    n = av.size - av.size % 4
+    av, bv = av[:n], bv[:n]
+    a, b, r = xgrid.Grid((n,), float), xgrid.Grid((n,), float), xgrid.Grid((n,), float)
+    a.now[:] = av
+    b.now[:] = bv
+    divide(r, a, b)
+    with np.errstate(all="ignore"):
+        want = av / bv
+    got = r.now
+    assert np.array_equal(got.view(np.uint64)[~np.isnan(want)], want.view(np.uint64)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))

@@ -41,6 +41,24 @@ template <class T> XGB_DEV T sq(T x) { return x * x; }
 
 // C semantics of the reference's int32 `/` and `%` are what CUDA C gives too.
 
+// IEEE-exact floating division with a shortcut for zero numerators: (+-0) / y for any
+// non-zero, non-NaN y is +-0 with sign = sign(x) xor sign(y).  div.rn.f64 sends every
+// zero / subnormal numerator through its special-operand subroutine (~10x the
+// instructions of the fast path); quiescent regions of a PDE field are exactly zero.
+XGB_DEV double fdiv(double x, double y) {
+    if (x == 0.0 && y != 0.0 && y == y)
+        return __longlong_as_double((__double_as_longlong(x) ^ __double_as_longlong(y)) &
+                                    (long long)0x8000000000000000ULL);
+    return x / y;
+}
+XGB_DEV float fdiv(float x, float y) {
+    if (x == 0.0f && y != 0.0f && y == y)
+        return __int_as_float((__float_as_int(x) ^ __float_as_int(y)) & (int)0x80000000u);
+    return x / y;
+}
+XGB_DEV double fdiv(double x, float y) { return fdiv(x, (double)y); }
+XGB_DEV double fdiv(float x, double y) { return fdiv((double)x, y); }
+
 // --------------------------------------------------------------------------- vector access
 template <int BYTES> struct Pack;
 template <> struct Pack<1>  { typedef uint8_t  type; };

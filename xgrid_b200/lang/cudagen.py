@@ -85,11 +85,21 @@ class ExprEmitter:
     """IR expression -> C text.  ``ident`` maps a scalar variable to its C
     spelling; ``tap`` maps a Stencil load to its C spelling."""
 
-    def __init__(self, module: "ModuleBuilder", ident, tap=None) -> None:
+    def __init__(self, module: "ModuleBuilder", ident, tap=None, hoist: dict | None = None) -> None:
         self.module, self.ident, self.tap = module, ident, tap
+        self.hoist = hoist          # C text -> name of a kernel-prologue constant (None = off)
 
     def __call__(self, e) -> str:
-        return getattr(self, "x_" + type(e).__name__)(e)
+        text = getattr(self, "x_" + type(e).__name__)(e)
+        if self.hoist is not None and isinstance(e, (ir.Binary, ir.Unary, ir.Condition, ir.Cast, ir.Call)) \
+                and _invariant(e):
+            # point-independent subexpression: evaluate once per thread instead of once per point
+            # (`auto` keeps the C type of the expression, so mixed-precision programs are unchanged)
+            name = self.hoist.get(text)
+            if name is None:
+                name = self.hoist[text] = f"h{len(self.hoist)}"
+            return name
+        return text
 
     def x_Constant(self, e: ir.Constant) -> str:
         return repr(e.value).lower()            # generator.py:393-394
@@ -111,6 +121,8 @@ class ExprEmitter:
                 ctype = "double" if wide else "float"
                 return f"xgb::sq<{ctype}>({base})"
             return f"{'pow' if wide else 'powf'}({base}, {self(e.right)})"
+        if e.operator == "/" and isinstance(e.left.type, Floating) and self.tap is not None:
+            return f"xgb::fdiv({self(e.left)}, {self(e.right)})"     # exact; see xgb_stencil.cuh
         return f"({self(e.left)} {e.operator} {self(e.right)})"
 
     def x_Condition(self, e: ir.Condition) -> str:
@@ -134,6 +146,21 @@ class ExprEmitter:
         if isinstance(e.operator, ir.Constructor):
             return f"({self.module.ctype(e.operator.type)}{{{args}}})"
         return f"{self.module.device_function(e.operator)}({args})"
+
+
+def _invariant(e) -> bool:
+    """True when the expression reads no grid and calls nothing that could write memory."""
+    for n in ir.walk_expr(e):
+        if isinstance(n, ir.Stencil):
+            return False
+        if isinstance(n, ir.Call) and not isinstance(n.operator, ir.Constructor):
+            if any(isinstance(t, Pointer) for _, t in n.operator.signature.arguments):
+                return False
+    return True
+
+
+def hoist_lines(hoist: dict, indent: str = "    ") -> list:
+    return [f"{indent}const auto {name} = {text};" for text, name in hoist.items()]
 
 
 # --------------------------------------------------------------------------- module
@@ -384,10 +411,11 @@ def _ident(var) -> str:
     return f"p.u_{var.name}"
 
 
-def _emit_statements(g: Group, module: ModuleBuilder, tap, lines: list, vexpr: str) -> None:
+def _emit_statements(g: Group, module: ModuleBuilder, tap, lines: list, vexpr: str,
+                     hoist: dict | None = None) -> None:
     """Per-point body: statement-at-a-time in program order, each predicated on
     the stored grid's mask value (generator.py:297-298)."""
-    emit = ExprEmitter(module, _ident, tap)
+    emit = ExprEmitter(module, _ident, tap, hoist)
     for a in g.stmts:
         sw = a.sweep
         store_level = "scratch" if g.implicit else sw.store.level
@@ -449,12 +477,14 @@ def _emit_windowed(g: Group, module: ModuleBuilder, V: int, variant: str) -> str
             L.append(f"    {module.ctype(s.elem)} o_{s.field}[V]; unsigned wr_{s.field} = 0u;")
     L.append("#pragma unroll")
     L.append("    for (int v = 0; v < V; ++v) {")
-    _emit_statements(g, module, tap, L, "v")
+    hoist: dict = {}
+    _emit_statements(g, module, tap, L, "v", hoist)
     L.append("    }")
     for s in g.slots:
         if s.written:
             L.append(f"    xgb::st_pred<{module.ctype(s.elem)}, V>(p.{s.field} + base, o_{s.field}, wr_{s.field});")
     L.append("}")
+    L[3:3] = hoist_lines(hoist)
     return "\n".join(L) + "\n"
 
 
@@ -629,7 +659,8 @@ def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
     L.append("#pragma unroll")
     L.append("        for (int v = 0; v < V; ++v) {")
     body: list = []
-    _emit_statements(g, module, tap, body, "v")
+    hoist: dict = {}
+    _emit_statements(g, module, tap, body, "v", hoist)
     L.extend("    " + b for b in body)
     L.append("        }")
     for s in g.slots:
@@ -643,6 +674,7 @@ def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
     L.append("    }")
     L.append("    #undef XGB_ROW")
     L.append("}")
+    L[3:3] = hoist_lines(hoist)
     return "\n".join(L) + "\n"
 
 
@@ -809,7 +841,8 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("#pragma unroll")
     L.append("            for (int v = 0; v < V; ++v) {")
     body: list = []
-    _emit_statements(g, module, tap, body, "v")
+    hoist: dict = {}
+    _emit_statements(g, module, tap, body, "v", hoist)
     L.extend("        " + b for b in body)
     L.append("            }")
     for s_ in g.slots:
@@ -822,4 +855,6 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("        ps = (ps + 1 == NS) ? 0 : ps + 1;")
     L.append("    }")
     L.append("}")
+    at = next(n for n, line in enumerate(L) if line.startswith("    const int ty = warp / WX"))
+    L[at:at] = hoist_lines(hoist)          # consumer warps only; the producer never needs them
     return "\n".join(L) + "\n"
