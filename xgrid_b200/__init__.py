@@ -66,11 +66,20 @@ def tick(grid: Any) -> None:
     ...
 
 
+def flush() -> None:
+    """Enqueue every deferred kernel call on the device stream (B200 extension).  Calls of
+    1-D kernels are deferred so that runs of identical calls can execute several time steps
+    per launch; reading ``Grid.now`` / ``.boundary`` flushes implicitly."""
+    from .lang.schedule import flush_pending
+    flush_pending()
+
+
 def synchronize() -> None:
-    """Block until every enqueued sweep has finished (B200 extension)."""
+    """Flush deferred calls and block until every enqueued sweep has finished (B200 extension)."""
     from .runtime.shim import Runtime
+    flush()
     Runtime.get().sync()
 
 
 __all__ = ["kernel", "function", "init", "ptr", "grid", "boundary", "c", "external", "Grid",
-           "shape", "dimension", "tick", "synchronize"]
+           "shape", "dimension", "tick", "synchronize", "flush"]

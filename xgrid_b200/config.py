@@ -12,6 +12,9 @@ New keyword-only extras (all optional):
 * ``distributed``-- slab-decompose grids over the ranks of the current
                     ``torch.distributed`` process group (one process per GPU).
 * ``graphs``     -- replay steady-state kernel calls from captured CUDA graphs.
+* ``temporal``   -- defer runs of identical calls of a 1-D kernel and execute them T time
+                    steps per launch from shared memory (temporal blocking); results are
+                    bit-identical to step-at-a-time execution.
 """
 from __future__ import annotations
 
@@ -40,6 +43,7 @@ class Configuration:
     distributed: bool = False
     graphs: bool = True
     strategy: str = "auto"
+    temporal: bool = True
 
     def __repr__(self) -> str:
         return repr(asdict(self))
@@ -75,7 +79,7 @@ def init(*, parallel: bool = True, cc: list[str] = ["gcc", "clang"], cacheroot: 
          comment: bool = False, overstep: Literal["none", "limit", "wrap"] = "none",
          opt_level: Literal[0, 1, 2, 3] = 2, precision: Literal["float", "double"] = "float",
          validate: bool = True, device: int | None = None, distributed: bool = False,
-         graphs: bool = True, strategy: str = "auto") -> None:
+         graphs: bool = True, strategy: str = "auto", temporal: bool = True) -> None:
     global _config, _epoch
     if sys.version_info < (3, 10):
         _log.fail(f"Minimum Python 3.10 is required, current version is {sys.version_info}")
@@ -86,6 +90,6 @@ def init(*, parallel: bool = True, cc: list[str] = ["gcc", "clang"], cacheroot: 
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     _config = Configuration(parallel, list(cc), cacheroot, comment, overstep, opt_level, precision,
-                            validate, device, distributed, graphs, strategy)
+                            validate, device, distributed, graphs, strategy, temporal)
     _epoch += 1
     _log.info(f"initialized with configuration: {_config}")

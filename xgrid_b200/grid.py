@@ -28,6 +28,13 @@ import numpy as np
 from .log import Logger
 from .types import Boolean, Floating, Grid as GridT, Integer, Structure, Value, parse_annotation
 
+def _flush() -> None:
+    """Execute deferred kernel calls (temporal-blocking queue) before grid state is observed."""
+    from .lang import schedule
+    if schedule._PENDING is not None:
+        schedule.flush_pending()
+
+
 SLACK = 64          # elements of linear slack before / after the padded array
 CHUNK = 128         # points per mask flag (XGB_CHUNK in xgb_stencil.cuh)
 ALIGN = 256
@@ -82,6 +89,7 @@ class Grid:
 
         self._ring: list[_Level] = [_Level(np.zeros(self.shape, self.numpy_dtype))]
         self._scratch: _Level | None = None
+        self._spares: list[_Level] = []
         self._boundary = np.zeros(self.shape, dtype=np.int32)
         self._mask_touched = True
         self._mask_snapshot = None
@@ -102,11 +110,13 @@ class Grid:
 
     @property
     def boundary(self) -> np.ndarray:
+        _flush()
         self._mask_touched = True
         return self._boundary
 
     @boundary.setter
     def boundary(self, value) -> None:
+        _flush()
         arr = np.asarray(value, dtype=np.int32)
         if arr.shape != self.shape:
             self.logger.dead("boundary mask has an incompatible shape")
@@ -126,6 +136,7 @@ class Grid:
     def fill(self, data: np.ndarray, time: int = 0) -> None:
         if data.shape != self.shape or data.dtype != self.numpy_dtype:
             self.logger.dead("Unable to fill grid with incompatible shape or data type")
+        _flush()
         k = abs(time)
         while len(self._ring) <= k:
             self._ring.append(_Level())
@@ -136,6 +147,7 @@ class Grid:
     @property
     def _data(self) -> list:
         """Host copies of every ring level, newest first (reference attribute)."""
+        _flush()
         return [self._host_view(k) for k in range(len(self._ring))]
 
     # ------------------------------------------------------------------ ring (operator.py:37-39)
@@ -147,6 +159,7 @@ class Grid:
         del self._ring[depth:]
 
     def _op_invoke(self, depth: int, tick: bool) -> None:
+        _flush()
         self._extend_time(depth)
         if tick:
             self._ring.insert(0, self._ring.pop())
@@ -182,6 +195,7 @@ class Grid:
         lv.dev = 0
 
     def _host_view(self, k: int) -> np.ndarray:
+        _flush()
         lv = self._ring[k]
         if lv.where == "zero":
             lv.host = np.zeros(self.shape, self.numpy_dtype)
@@ -223,6 +237,9 @@ class Grid:
         if self._scratch is not None:
             self._release(self._scratch)
             self._scratch = None
+        for lv in self._spares:
+            self._release(lv)
+        self._spares = []
         self._ghost = rows
 
     def _prepare_device(self, ghost_rows: int = 1) -> None:
@@ -240,6 +257,15 @@ class Grid:
             self._alloc_level(self._scratch)
             self._scratch.where = "device"
         return self._scratch
+
+    def _spare_levels(self, n: int) -> list:
+        """Extra device levels owned by the grid (outputs of the multi-step kernels)."""
+        while len(self._spares) < n:
+            lv = _Level()
+            self._alloc_level(lv)
+            lv.where = "device"
+            self._spares.append(lv)
+        return self._spares[:n]
 
     def _swap_scratch(self) -> None:
         """Jacobi double buffer: the scratch level becomes level 0."""
@@ -331,6 +357,8 @@ class Grid:
                 self._release(lv)
             if self._scratch is not None:
                 self._release(self._scratch)
+            for lv in self._spares:
+                self._release(lv)
             for ptr, _ in self._lists.values():
                 if ptr:
                     rt.free(ptr)

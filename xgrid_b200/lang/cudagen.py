@@ -26,6 +26,7 @@ VARIANT_DENSE = "dense"
 VARIANT_SPARSE = "sparse"
 VARIANT_MARCH = "march"
 VARIANT_TILED = "tiled"
+VARIANT_MULTISTEP = "multistep"
 MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
 import os as _os
 MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "2"))   # rows loaded ahead of use per chain
@@ -68,6 +69,7 @@ class Group:
     halo_last: int = 0
     march: bool = False                           # has axis-0 marching variants
     tiled: dict | None = None                     # geometry of the async shared-memory pipeline variant
+    multistep: dict | None = None                 # temporal-blocking variant (1-D, whole-kernel groups)
 
     def slot(self, grid: str, level) -> Slot:
         for s in self.slots:
@@ -339,6 +341,8 @@ def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims:
     for m in g.masks:
         add("const uint8_t* __restrict__", f"m_{m}", ctypes.c_void_p)
         add("const uint8_t* __restrict__", f"f_{m}", ctypes.c_void_p)
+    for a in range(4):
+        add("void*", f"aux{a}", ctypes.c_void_p)  # extra level pointers of the multi-step variant
     add("const int64_t* __restrict__", "list", ctypes.c_void_p)
     add("int64_t", "count", ctypes.c_int64)
     add("int64_t", "chunk0", ctypes.c_int64)     # axis-0 points per CTA in the marching variant
@@ -395,6 +399,9 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
                 g.tiled = tiled_config(g)
                 if g.tiled is not None:
                     module.kernels.append(_emit_tiled(g, module, g.tiled))
+            g.multistep = multistep_config(g)
+            if g.multistep is not None:
+                module.kernels.append(_emit_multistep(g, module, g.multistep))
         else:
             module.kernels.append(_emit_general(g, module, VARIANT_DENSE))
             module.kernels.append(_emit_general(g, module, VARIANT_SPARSE))
@@ -857,4 +864,125 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("}")
     at = next(n for n, line in enumerate(L) if line.startswith("    const int ty = warp / WX"))
     L[at:at] = hoist_lines(hoist)          # consumer warps only; the producer never needs them
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------- multi-step (temporal blocking) variant
+MULTISTEP_T = int(_os.environ.get("XGB_MS_T", "64"))
+MULTISTEP_W = int(_os.environ.get("XGB_MS_W", "4096"))
+
+
+def multistep_config(g: Group):
+    """1-D groups that read only the previous level of the ONE grid they update can run T
+    time steps per launch from shared memory."""
+    if g.ndim != 1 or g.implicit or g.sparse:
+        return None
+    grids = {s.grid for s in g.slots}
+    if len(grids) != 1:
+        return None
+    levels = {(s.level, s.read, s.written) for s in g.slots}
+    if levels != {(0, False, True), (1, True, False)}:
+        return None
+    elem = g.slots[0].elem
+    if isinstance(elem, (Structure, Boolean)) or elem.width_bytes not in (4, 8):
+        return None
+    h = max(1, g.halo_last)
+    T = MULTISTEP_T
+    while T * h > 64:                 # halo must stay inside the level's zero slack
+        T //= 2
+    T -= T % 2                        # even: the ring order after T ticks equals the order before
+    if T < 4:
+        return None
+    W, H = MULTISTEP_W, T * h
+    L = W + 2 * H
+    return {"T": T, "W": W, "H": H, "h": h, "L": L, "threads": 512, "V": 16 // elem.width_bytes,
+            "smem": 2 * L * elem.width_bytes + L + 64}
+
+
+def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
+    """T steps per launch.  Two shared-memory buffers start as copies of the two ring levels
+    (now / previous) of a W+2H window; every step writes the *older* buffer where a statement's
+    mask matches -- exactly what T ticks + T sweeps do to the ring (unwritten points keep the value
+    from two steps back) -- and the window of valid points shrinks by h per step."""
+    elem = g.slots[0].elem
+    T_ = module.ctype(elem)
+    gname = g.slots[0].grid
+
+    def tap(e: ir.Stencil) -> str:
+        return f"cur[q + ({e.space_offset[-1]})]"
+
+    def stmts(masked: bool, hoist: dict) -> list:
+        emit = ExprEmitter(module, _ident, tap, hoist)
+        out = []
+        for a in g.stmts:
+            rhs = emit(a.value)
+            if masked:
+                out.append(f"if (m == {a.sweep.mask}) nxt[q] = {rhs};")
+            elif a.sweep.mask == 0:
+                out.append(f"nxt[q] = {rhs};")
+        return out
+
+    hoist: dict = {}
+    fast, slow = stmts(False, hoist), stmts(True, hoist)
+    name = kernel_name(g, VARIANT_MULTISTEP, 1)
+    L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int T = {c['T']}, HS = {c['h']}, H = {c['H']}, W = {c['W']}, L = {c['L']}, NT = {c['threads']}, V = {c['V']};")
+    L.append(f"    typedef {T_} E;")
+    L.extend(hoist_lines(hoist))
+    L.append("    extern __shared__ __align__(16) unsigned char xgb_smem[];")
+    L.append("    E *b0 = reinterpret_cast<E *>(xgb_smem);      // starts as the current level  (u^n)")
+    L.append("    E *b1 = b0 + L;                               // starts as the previous level (u^{n-1})")
+    L.append("    uint8_t *sm = reinterpret_cast<uint8_t *>(b1 + L);")
+    L.append("    const E *now = static_cast<const E *>(p.aux0), *prev = static_cast<const E *>(p.aux1);")
+    L.append("    E *out0 = static_cast<E *>(p.aux2), *out1 = static_cast<E *>(p.aux3);")
+    L.append("    const int64_t g0 = (int64_t)blockIdx.x * W - H;   // global index of window element 0")
+    L.append("    for (int q = threadIdx.x * V; q < L; q += NT * V) {")
+    L.append("        E a[V], b[V];")
+    L.append("        const int64_t gi = g0 + q;                 // stay inside the level's zero slack")
+    L.append("        if (gi >= -64 && gi + V <= p.n0 + 64) { xgb::ld_vec<E, V>(now + gi, a); xgb::ld_vec<E, V>(prev + gi, b); }")
+    L.append("        else { for (int v = 0; v < V; ++v) { a[v] = E(0); b[v] = E(0); } }")
+    L.append("#pragma unroll")
+    L.append("        for (int v = 0; v < V; ++v) { b0[q + v] = a[v]; b1[q + v] = b[v]; }")
+    L.append("    }")
+    L.append("    int any = 0;")
+    L.append("    for (int q = threadIdx.x; q < L; q += NT) {")
+    L.append("        const int64_t gi = g0 + q;")
+    L.append(f"        int m = 255;                                  // outside the grid: never updated")
+    L.append(f"        if (gi >= 0 && gi < p.n0) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
+    L.append("        sm[q] = (uint8_t)m; any |= m;")
+    L.append("    }")
+    L.append("    const int masked = __syncthreads_or(any);")
+    L.append("    E *cur = b0, *nxt = b1;")
+    L.append("    if (!masked) {")
+    L.append("        for (int s = 1; s <= T; ++s) {")
+    L.append("#pragma unroll 4")
+    L.append("            for (int q = s * HS + threadIdx.x; q < L - s * HS; q += NT) {")
+    L.extend("                " + x for x in fast)
+    L.append("            }")
+    L.append("            __syncthreads();")
+    L.append("            E *t = cur; cur = nxt; nxt = t;")
+    L.append("        }")
+    L.append("    } else {")
+    L.append("        for (int s = 1; s <= T; ++s) {")
+    L.append("            for (int q = s * HS + threadIdx.x; q < L - s * HS; q += NT) {")
+    L.append("                const int m = sm[q];")
+    L.extend("                " + x for x in slow)
+    L.append("            }")
+    L.append("            __syncthreads();")
+    L.append("            E *t = cur; cur = nxt; nxt = t;")
+    L.append("        }")
+    L.append("    }")
+    L.append("    // T is even: b0 holds u^{n+T}, b1 holds u^{n+T-1}")
+    L.append("    for (int q = H + threadIdx.x * V; q < H + W; q += NT * V) {")
+    L.append("        const int64_t gi = g0 + q;")
+    L.append("        if (gi + V <= p.n0) {")
+    L.append("            E a[V], b[V];")
+    L.append("#pragma unroll")
+    L.append("            for (int v = 0; v < V; ++v) { a[v] = b0[q + v]; b[v] = b1[q + v]; }")
+    L.append("            xgb::st_vec<E, V>(out0 + gi, a); xgb::st_vec<E, V>(out1 + gi, b);")
+    L.append("        } else {")
+    L.append("            for (int v = 0; v < V; ++v) if (gi + v < p.n0) { out0[gi + v] = b0[q + v]; out1[gi + v] = b1[q + v]; }")
+    L.append("        }")
+    L.append("    }")
+    L.append("}")
     return "\n".join(L) + "\n"

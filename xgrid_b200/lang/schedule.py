@@ -352,6 +352,20 @@ class _Interpreter:
             raise Exception("unsupported assignment target")
 
 
+# --------------------------------------------------------------------------- deferred calls (temporal blocking)
+_PENDING = None          # {"program", "args", "grid", "key", "count"}: identical calls not yet executed
+PENDING_LIMIT = 4096
+MULTISTEP_MIN_POINTS = int(os.environ.get("XGB_MS_MIN", "16384"))
+
+
+def flush_pending() -> None:
+    """Execute the deferred run of identical kernel calls, T time steps per launch."""
+    global _PENDING
+    p, _PENDING = _PENDING, None
+    if p is not None:
+        p["program"]._run_batch(p["args"], p["grid"], p["count"])
+
+
 # --------------------------------------------------------------------------- Program
 class Program:
     """A compiled kernel: plan + generated module + launch logic."""
@@ -379,6 +393,19 @@ class Program:
         self.source = self.module_builder.source() if self.groups else ""
         self._module = None
         self._functions: dict = {}
+        # temporal blocking: the whole kernel is scalar prologue + ONE 1-D group on one grid
+        self.batchable = False
+        self._grid_pos = -1
+        if (len(self.groups) == 1 and self.groups[0].multistep is not None and self.depth == 2
+                and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
+                and isinstance(self.ir.signature.return_type, Void)
+                and isinstance(self.plan[-1], GroupNode)
+                and all(isinstance(n, tuple) and n[0] == "stmt" and isinstance(n[1], ir.Assignment)
+                        for n in self.plan[:-1])
+                and not any(isinstance(t, (Pointer, Structure)) for _, t in self.ir.signature.arguments)):
+            self.batchable = True
+            self._grid_pos = [n for n, (_, t) in enumerate(self.ir.signature.arguments)
+                              if isinstance(t, GridT)][0]
         self._graphs: dict = {}
         self._seen: set = set()
         self._image = None
@@ -427,11 +454,33 @@ class Program:
 
     # ---- call
     def __call__(self, *args):
+        global _PENDING
         sig = self.ir.signature.arguments
         if len(args) != len(sig):
             # xgrid/util/ffi.py:31-33
             raise TypeError(f"this function takes {len(sig)} argument ({len(args)} given)")
+        if self.batchable and self.config.temporal:
+            # defer: a run of identical calls is executed T steps per launch on flush
+            grid = args[self._grid_pos]
+            if (getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and not grid.sharded
+                    and grid.dimension == 1):
+                key = tuple(a for n, a in enumerate(args) if n != self._grid_pos)
+                p = _PENDING
+                if p is not None and p["program"] is self and p["grid"] is grid and p["key"] == key \
+                        and p["count"] < PENDING_LIMIT:
+                    p["count"] += 1
+                    return None
+                flush_pending()
+                self._bind(args)        # type / arity errors surface at the call site
+                _PENDING = {"program": self, "args": args, "grid": grid, "key": key, "count": 1}
+                return None
+        if _PENDING is not None:
+            flush_pending()
+        return self._call_now(args)
+
+    def _bind(self, args):
         from ..grid import Grid
+        sig = self.ir.signature.arguments
         env, grids = {}, {}
         for (name, t), a in zip(sig, args):
             if isinstance(t, GridT):
@@ -448,6 +497,11 @@ class Program:
                 env[name] = a
             else:
                 env[name] = coerce(t, a)
+        return env, grids
+
+    def _call_now(self, args):
+        sig = self.ir.signature.arguments
+        env, grids = self._bind(args)
         # tick the field and resize the time ring (xgrid/lang/operator.py:37-39)
         for (name, t), a in zip(sig, args):
             if isinstance(t, GridT):
@@ -501,6 +555,47 @@ class Program:
     def _runtime(self):
         from ..runtime.shim import Runtime
         return Runtime.get()
+
+    def _run_batch(self, args, grid, count: int) -> None:
+        """`count` deferred identical calls.  While at least T remain, one launch of the
+        multi-step kernel advances T time steps: it reads the two ring levels, iterates in
+        shared memory and writes the two newest levels into spare buffers that then become
+        the ring (T is even, so the ring order equals the order after T single ticks)."""
+        g = self.groups[0]
+        cfg = g.multistep
+        T = cfg["T"]
+        done = 0
+        if count >= T:
+            env, grids = self._bind(args)
+            captured = []
+            _Interpreter(self.ir, env, grids, lambda grp, e: captured.append(dict(e))).run(self.plan)
+            env = captured[0]
+            rt = self._runtime()
+            grid._extend_time(2)
+            grid._prepare_device(1)
+            fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_MULTISTEP, 1), cfg["smem"])
+            P = g.params_cls()
+            P.n0 = grid.shape[0]
+            P.rows, P.cols = 1, grid.shape[0]
+            gname = g.slots[0].grid
+            setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
+            setattr(P, f"f_{gname}", grid._flags_dev if grid._mask_any else None)
+            from .launch import Launcher
+            marshal = Launcher(self, grids)
+            for name, t in g.scalars.items():
+                setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
+            blocks = (grid.shape[0] + cfg["W"] - 1) // cfg["W"]
+            while count - done >= T:
+                x0, x1 = grid._ring[0], grid._ring[1]
+                c, d = grid._spare_levels(2)
+                P.aux0, P.aux1, P.aux2, P.aux3 = x0.dev, x1.dev, c.dev, d.dev
+                rt.launch(fn, (blocks, 1, 1), (cfg["threads"], 1, 1), P, smem=cfg["smem"])
+                grid._ring, grid._spares = [c, d], [x0, x1]
+                c.where = d.where = "device"
+                c.halo_ok = d.halo_ok = False
+                done += T
+        for _ in range(count - done):
+            self._call_now(args)
 
     def _graph_key(self, env: dict, grids: dict):
         """Everything a recorded call depends on: scalar argument values, the

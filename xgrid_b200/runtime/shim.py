@@ -176,10 +176,18 @@ class Runtime:
         return f.value, t.value
 
     # ---- streams / events
+    @staticmethod
+    def _flush_deferred() -> None:
+        from ..lang import schedule
+        if schedule._PENDING is not None:
+            schedule.flush_pending()
+
     def sync(self, stream: int = 0) -> None:
+        self._flush_deferred()
         check(self.l.xgb_stream_sync(stream))
 
     def device_sync(self) -> None:
+        self._flush_deferred()
         check(self.l.xgb_device_sync())
 
     def stream_create(self) -> int:
@@ -198,6 +206,7 @@ class Runtime:
         return h.value
 
     def event_record(self, ev: int, stream: int = 0) -> None:
+        self._flush_deferred()      # deferred kernel calls belong before the event
         check(self.l.xgb_event_record(ev, stream))
 
     def event_sync(self, ev: int) -> None:
