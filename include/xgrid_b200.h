@@ -68,6 +68,9 @@ int xgb_mem_info(uint64_t *free_bytes, uint64_t *total_bytes);
 /* ---- streams / events --------------------------------------------------- */
 /* stream 0 is the backend's default compute stream (created by xgb_init). */
 int xgb_stream_create(xgb_handle *stream);
+/* high_priority != 0: greatest stream priority (halo-exchange stream, so that NCCL kernels
+ * are scheduled ahead of the interior sweep they overlap with) */
+int xgb_stream_create_ex(xgb_handle *stream, int high_priority);
 int xgb_stream_destroy(xgb_handle stream);
 int xgb_stream_sync(xgb_handle stream);
 int xgb_stream_raw(xgb_handle stream, void **cuda_stream); /* cudaStream_t for interop */

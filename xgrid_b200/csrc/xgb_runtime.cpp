@@ -322,6 +322,16 @@ int xgb_stream_create(xgb_handle *stream) {
     return 0;
 }
 
+int xgb_stream_create_ex(xgb_handle *stream, int high_priority) {
+    if (require_init()) return 1;
+    int lo = 0, hi = 0;
+    XGB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    XGB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    *stream = reinterpret_cast<xgb_handle>(s);
+    return 0;
+}
+
 int xgb_stream_destroy(xgb_handle stream) {
     if (g_device < 0 || stream == 0) return 0;
     XGB_CUDA(cudaStreamDestroy(as_stream(stream)));

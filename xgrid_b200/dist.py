@@ -98,6 +98,9 @@ class NcclTransport:
         self.topo = topo
         self.shim = shim
         self.rt = shim.Runtime.get()
+        self._comm_stream = None
+        self._events: list = []
+        self._next = 0
         lib = shim.lib()
         nccl_path = ""
         try:     # use the very libnccl torch already mapped into this process
@@ -129,6 +132,31 @@ class NcclTransport:
         buf = ctypes.create_string_buffer(bytes(raw), 128)
         shim.check(lib.xgb_nccl_init(ctypes.cast(buf, ctypes.c_void_p), topo.rank, topo.world))
         _log.info(f"NCCL halo transport ready: rank {topo.rank}/{topo.world}")
+
+    def exchange_async(self, items: list) -> None:
+        """Exchange on the high-priority comm stream, ordered after everything enqueued on the
+        compute stream so far; readers wait on ``level.halo_event`` (launch.py)."""
+        if not items:
+            return
+        rt = self.rt
+        if self._comm_stream is None:
+            self._comm_stream = rt.stream_create(high_priority=True)
+        ready = self._event()
+        rt.event_record_raw(ready, 0)
+        rt.stream_wait_event(self._comm_stream, ready)
+        self.exchange(items, self._comm_stream)
+        done = self._event()
+        rt.event_record_raw(done, self._comm_stream)
+        for _, lv, _ in items:
+            lv.halo_event = done
+
+    def _event(self) -> int:
+        """Round-robin pool of events (an event is reused long after its waiters ran)."""
+        if len(self._events) < 64:
+            self._events.append(self.rt.event_create())
+            return self._events[-1]
+        self._next = (self._next + 1) % len(self._events)
+        return self._events[self._next]
 
     def exchange(self, items: list, stream: int = 0) -> None:
         """items: [(grid, level, h)] -- refresh h ghost rows on both sides of each level."""

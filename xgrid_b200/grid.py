@@ -48,7 +48,7 @@ def parse_numpy_dtype(t: Value):
 
 class _Level:
     """One time level: device allocation + optional host mirror."""
-    __slots__ = ("dev", "host", "where", "raw", "halo_ok")
+    __slots__ = ("dev", "host", "where", "raw", "halo_ok", "halo_event", "pinned")
 
     def __init__(self, host=None) -> None:
         self.dev = 0            # device pointer of the first *real* element (0 = not allocated)
@@ -56,6 +56,8 @@ class _Level:
         self.where = "host" if host is not None else "zero"
         self.raw = 0            # base of the padded device allocation
         self.halo_ok = False    # ghost rows hold the neighbours' current rows (sharded grids)
+        self.pinned = 0         # address of the page-locked host mirror (0 = pageable)
+        self.halo_event = 0     # event of a halo exchange still in flight on the comm stream
 
 
 class Grid:
@@ -188,11 +190,32 @@ class Grid:
         lv.raw = raw
 
     def _release(self, lv: _Level) -> None:
+        self._unpin(lv)
         if lv.dev and self._rt is not None:
             self._rt.free(lv.raw)
             if lv.raw in self._allocs:
                 self._allocs.remove(lv.raw)
         lv.dev = 0
+
+    PIN_MIN_BYTES = 1 << 20
+
+    def _pin(self, lv: _Level) -> None:
+        """Page-lock a host mirror once so H2D / D2H run at full PCIe speed."""
+        if lv.host is None or lv.host.nbytes < self.PIN_MIN_BYTES:
+            return
+        addr = lv.host.ctypes.data
+        if lv.pinned == addr:
+            return
+        self._unpin(lv)
+        from .runtime import shim
+        if shim.lib().xgb_host_register(ctypes.c_void_p(addr), lv.host.nbytes) == 0:
+            lv.pinned = addr
+
+    def _unpin(self, lv: _Level) -> None:
+        if lv.pinned:
+            from .runtime import shim
+            shim.lib().xgb_host_unregister(ctypes.c_void_p(lv.pinned))
+            lv.pinned = 0
 
     def _host_view(self, k: int) -> np.ndarray:
         _flush()
@@ -203,6 +226,7 @@ class Grid:
             if lv.host is None:
                 lv.host = np.empty(self.shape, self.numpy_dtype)
             rt = self._runtime()
+            self._pin(lv)
             rt.d2h(lv.host.ctypes.data, lv.dev, self.size * self.itemsize)
             rt.sync()
         # the caller may write through the returned array: the host owns the level now
@@ -217,13 +241,16 @@ class Grid:
                 return
         if lv.where == "host":
             host = np.ascontiguousarray(lv.host)
-            self._runtime().h2d(lv.dev, host.ctypes.data, self.size * self.itemsize)
-            # pageable copies are staged synchronously by the driver; keep `host` alive anyway
             lv.host = host
+            self._pin(lv)
+            self._runtime().h2d(lv.dev, host.ctypes.data, self.size * self.itemsize)
+            if lv.pinned:
+                self._runtime().sync()      # the caller may modify the mirror right after
         elif lv.where == "zero":
             self._runtime().memset(lv.dev, 0, self.size * self.itemsize)
         lv.where = "device"
         lv.halo_ok = False
+        lv.halo_event = 0
 
     def _ensure_ghost(self, rows: int) -> None:
         if rows <= self._ghost:

@@ -346,6 +346,8 @@ def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims:
     add("const int64_t* __restrict__", "list", ctypes.c_void_p)
     add("int64_t", "count", ctypes.c_int64)
     add("int64_t", "chunk0", ctypes.c_int64)     # axis-0 points per CTA in the marching variant
+    add("int64_t", "r_lo", ctypes.c_int64)       # axis-0 range [r_lo, r_hi) swept by this launch
+    add("int64_t", "r_hi", ctypes.c_int64)       # (march / tiled variants; edge-first launches of a slab)
     add("int64_t", "rows", ctypes.c_int64)
     add("int64_t", "cols", ctypes.c_int64)
     for a in range(g.ndim):
@@ -613,16 +615,16 @@ def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
         L.append("    const int64_t j_raw = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;")
         L.append("    const bool act = act_c && (j_raw < p.n1);")
         L.append("    const int64_t j = j_raw < p.n1 ? j_raw : (p.n1 - 1);")
-        L.append("    const int64_t i0 = (int64_t)blockIdx.z * p.chunk0;")
+        L.append("    const int64_t i0 = p.r_lo + (int64_t)blockIdx.z * p.chunk0;")
         L.append("    const int64_t S0 = p.n1 * p.n2;")
         L.append("    int64_t base = i0 * S0 + j * p.cols + col;")
     else:
         L.append("    const bool act = act_c;")
-        L.append("    const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
+        L.append("    const int64_t i0 = p.r_lo + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
         L.append("    const int64_t S0 = p.cols;")
         L.append("    int64_t base = i0 * S0 + col;")
-    L.append("    if (i0 >= p.n0) return;")
-    L.append("    const int64_t iend = (i0 + p.chunk0 < p.n0) ? (i0 + p.chunk0) : p.n0;")
+    L.append("    if (i0 >= p.r_hi) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.r_hi) ? (i0 + p.chunk0) : p.r_hi;")
     # chain registers + prologue (all but the leading row of every chain)
     PF = MARCH_PREFETCH
     for ch in chains.values():
@@ -772,14 +774,14 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("    const int64_t c0 = (int64_t)blockIdx.x * W;")
     if nd == 3:
         L.append("    const int64_t j0 = (int64_t)blockIdx.y * TJ;")
-        L.append("    const int64_t i0 = (int64_t)blockIdx.z * p.chunk0;")
+        L.append("    const int64_t i0 = p.r_lo + (int64_t)blockIdx.z * p.chunk0;")
         L.append("    const int64_t S0 = p.n1 * p.n2;")
     else:
         L.append("    const int64_t j0 = 0;")
-        L.append("    const int64_t i0 = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
+        L.append("    const int64_t i0 = p.r_lo + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
         L.append("    const int64_t S0 = p.cols;")
-    L.append("    if (i0 >= p.n0) return;")
-    L.append("    const int64_t iend = (i0 + p.chunk0 < p.n0) ? (i0 + p.chunk0) : p.n0;")
+    L.append("    if (i0 >= p.r_hi) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.r_hi) ? (i0 + p.chunk0) : p.r_hi;")
     L.append("    const int planes = (int)(iend - i0) + DSPAN;          // input planes this CTA streams")
     L.append("    if (threadIdx.x == 0) {")
     L.append("        for (int s = 0; s < NS; ++s) { xgb::pipe::mbar_init(&full[s], 1); xgb::pipe::mbar_init(&empty[s], NCW); }")

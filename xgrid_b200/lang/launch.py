@@ -45,6 +45,7 @@ TUNE = {
     "vec_bytes": int(os.environ.get("XGB_VEC_BYTES", "32")),
     "march": os.environ.get("XGB_MARCH", "1") != "0",
     "tiled": os.environ.get("XGB_TILED", "1") != "0",
+    "overlap": os.environ.get("XGB_OVERLAP", "1") != "0",
     "tx": int(os.environ.get("XGB_TX", "0")),
     "ty": int(os.environ.get("XGB_TY", "0")),
     "chunk0": int(os.environ.get("XGB_CHUNK0", "0")),
@@ -158,6 +159,7 @@ class Launcher:
                 variant = cudagen.VARIANT_SPARSE
                 ptr, count = lead._index_list(k)
                 P.list, P.count = ptr, count
+        P.r_lo, P.r_hi = 0, shape[0]
         if variant == cudagen.VARIANT_DENSE:
             vmax = max(1, TUNE["vec_bytes"] // max(s.elem.width_bytes if hasattr(s.elem, "width_bytes") else 16
                                                    for s in g.slots))
@@ -169,35 +171,72 @@ class Launcher:
             if (t is not None and TUNE["tiled"] and cols % t["V"] == 0 and cols >= t["W"] and shape[0] >= 16
                     and (g.ndim == 2 or shape[1] >= t["TJ"])):
                 variant, V = cudagen.VARIANT_TILED, t["V"]
-                grid_dim, block_dim, P.chunk0 = tiled_geometry(shape, t)
                 smem = t["smem"]
             elif g.march and V > 1 and TUNE["march"] and shape[0] >= 4:
                 variant = cudagen.VARIANT_MARCH
-                grid_dim, block_dim, P.chunk0 = march_geometry(shape, V, cudagen.MARCH_ROWS[g.ndim])
+        fn = self.program.function(cudagen.kernel_name(g, variant, V), smem)
+
+        def launch_rows(lo: int, hi: int) -> None:
+            """One launch of the chosen variant over axis-0 rows [lo, hi)."""
+            if hi <= lo:
+                return
+            sub = (hi - lo,) + tuple(shape[1:])
+            P.r_lo, P.r_hi = lo, hi
+            if variant == cudagen.VARIANT_TILED:
+                grid_dim, block_dim, P.chunk0 = tiled_geometry(sub, g.tiled)
+            elif variant == cudagen.VARIANT_MARCH:
+                grid_dim, block_dim, P.chunk0 = march_geometry(sub, V, cudagen.MARCH_ROWS[g.ndim])
+            elif variant == cudagen.VARIANT_SPARSE:
+                block_dim, grid_dim = (128, 1, 1), ((P.count + 127) // 128, 1, 1)
             else:
                 grid_dim, block_dim = dense_geometry(rows, cols, V)
+            self.rt.launch(fn, grid_dim, block_dim, P, smem=smem)
+            self.launches += 1
+
+        written = [(self.grids[s.grid], s) for s in g.slots if s.written]
+        edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)
+        if (edge and TUNE["overlap"] and variant in (cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH)
+                and shape[0] >= 8 * edge):
+            # slab edges first, then ship the fresh rows to the neighbours on the comm stream
+            # while the interior of the slab is still being swept
+            from .. import dist
+            launch_rows(0, edge)
+            launch_rows(shape[0] - edge, shape[0])
+            self._mark_written(g)
+            items = []
+            for gr, s in written:
+                if gr.sharded:
+                    lv = gr._scratch if s.level == "scratch" else gr._ring[s.level]
+                    items.append((gr, lv, edge))
+            dist.transport().exchange_async(items)
+            launch_rows(edge, shape[0] - edge)
         else:
-            block_dim = (128, 1, 1)
-            grid_dim = ((P.count + 127) // 128, 1, 1)
-        fn = self.program.function(cudagen.kernel_name(g, variant, V), smem)
-        self.rt.launch(fn, grid_dim, block_dim, P, smem=smem)
-        self.launches += 1
-        for s in g.slots:
-            if s.written:
-                grid = self.grids[s.grid]
-                (grid._scratch if s.level == "scratch" else grid._ring[s.level]).halo_ok = False
+            launch_rows(0, shape[0])
+            self._mark_written(g)
         if g.implicit:
             self.grids[g.stmts[0].sweep.grid.name]._swap_scratch()
 
+    def _mark_written(self, g: cudagen.Group) -> None:
+        for s in g.slots:
+            if s.written:
+                grid = self.grids[s.grid]
+                lv = grid._scratch if s.level == "scratch" else grid._ring[s.level]
+                lv.halo_ok = False
+                lv.halo_event = 0
+
     def _refresh_halos(self, g: cudagen.Group) -> None:
-        """Sharded grids: import the neighbours' rows into the ghost rows of every level
-        this group reads at a non-zero axis-0 offset and that changed since its last exchange."""
+        """Sharded grids: before this group reads a level at a non-zero axis-0 offset its ghost
+        rows must hold the neighbours' rows: wait for an exchange already in flight (started
+        right after the level's edges were written), or exchange now if the level is stale."""
         from .. import dist
         reads = []
         for s in g.slots:
             if s.read and s.halo0 > 0:
                 grid = self.grids[s.grid]
                 lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
+                if grid.sharded and lv.halo_ok and lv.halo_event:
+                    self.rt.stream_wait_event(0, lv.halo_event)
+                    lv.halo_event = 0
                 reads.append((grid, lv, s.halo0))
         stale = dist.HaloPlan.stale(reads)
         if stale:

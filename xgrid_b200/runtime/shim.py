@@ -53,6 +53,7 @@ SIGNATURES = {
     "xgb_host_unregister": [c_void_p],
     "xgb_mem_info": [POINTER(c_uint64), POINTER(c_uint64)],
     "xgb_stream_create": [POINTER(Handle)],
+    "xgb_stream_create_ex": [POINTER(Handle), c_int],
     "xgb_stream_destroy": [Handle],
     "xgb_stream_sync": [Handle],
     "xgb_stream_raw": [Handle, POINTER(c_void_p)],
@@ -190,9 +191,9 @@ class Runtime:
         self._flush_deferred()
         check(self.l.xgb_device_sync())
 
-    def stream_create(self) -> int:
+    def stream_create(self, high_priority: bool = False) -> int:
         h = Handle()
-        check(self.l.xgb_stream_create(C.byref(h)))
+        check(self.l.xgb_stream_create_ex(C.byref(h), 1 if high_priority else 0))
         return h.value
 
     def stream_raw(self, stream: int = 0) -> int:
@@ -207,6 +208,10 @@ class Runtime:
 
     def event_record(self, ev: int, stream: int = 0) -> None:
         self._flush_deferred()      # deferred kernel calls belong before the event
+        check(self.l.xgb_event_record(ev, stream))
+
+    def event_record_raw(self, ev: int, stream: int = 0) -> None:
+        """Record without flushing the deferred-call queue (internal stream plumbing)."""
         check(self.l.xgb_event_record(ev, stream))
 
     def event_sync(self, ev: int) -> None:
