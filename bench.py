@@ -301,6 +301,15 @@ def run_ours(args, rank: int, world: int):
     peak, peak_src = measured_peaks()
     alg_bytes = points * spec["bytes_pt"]
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(name)
+        if t and tuple(shape) == tuple(spec["shape"]):
+            traffic = t["bytes_per_launch"]
+            traffic_src = f"{t['kernel']}: DRAM read+write per launch ({t['steps_per_launch']} step(s)), {t['source']}"
+    except OSError:
+        pass
     line = {
         "metric": "stencil Gpoint-updates/s", "value": value, "unit": "Gpoint-updates/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step,
@@ -311,7 +320,8 @@ def run_ours(args, rank: int, world: int):
                    "l2": "working set (2 levels) larger than the 126 MB L2" if points * 16 > 126e6 else "L2-resident (small grid)",
                    "validate_build": True},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg_bytes,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "gpu_launches": int(launches),

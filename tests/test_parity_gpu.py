@@ -286,3 +286,98 @@ def test_multistep_changing_scalars_flushes(k64):
         oracle.step_conv1d(h, 1.0, dt, dx)
     eq(u._data[0], h._data[0])
     eq(u._data[1], h._data[1])
+
+
+# --------------------------------------------------------------------------- BASELINE.json sizes
+def _free_host_gib():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / (1 << 20)
+    except OSError:
+        pass
+    return 0.0
+
+
+def test_full_size_conv1d_2p24(k64):
+    """config[1]: 2^24 points; 150 steps (2 fused 64-step launches + 22 single steps) vs the oracle."""
+    n = 1 << 24
+    ic, dx = W.ic_1d(n)
+    u, h = make_grid(ic), HostGrid((n,))
+    h.now[...] = ic
+    u.boundary[0] = 1
+    h.boundary[0] = 1
+    for _ in range(150):
+        k64["convection_1d"](u, 1.0, 0.5 * dx, dx)
+        oracle.step_conv1d(h, 1.0, 0.5 * dx, dx)
+    eq(u._data[0], h._data[0], "L0")
+    eq(u._data[1], h._data[1], "L1")
+
+
+def test_full_size_conv2d_16384(k64):
+    """config[2]: 16384^2 fp64, 2 steps, bit-exact vs the oracle (the reference's own limit is
+    ~0.5 s/step here)."""
+    if _free_host_gib() < 24:
+        pytest.skip("needs ~24 GiB of host memory")
+    n = 16384
+    dx = 2.0 / (n - 1)
+    ic = np.ones((n, n))
+    ic[n // 4:n // 2, n // 4:n // 2] = 2.0
+    ic += np.linspace(0.0, 1e-3, n)[None, :]
+    mask = np.zeros((n, n), np.int32)
+    mask[0, :] = 1
+    mask[:, 0] = 1
+    u, h = make_grid(ic, mask), HostGrid((n, n))
+    h.now[...] = ic
+    h.boundary[...] = mask
+    for _ in range(2):
+        k64["convection_2d"](u, 1.0, 0.5 * dx, dx, dx)
+        oracle.step_conv2d(h, 1.0, 0.5 * dx, dx, dx)
+    eq(u._data[0], h._data[0], "L0")
+    eq(u._data[1], h._data[1], "L1")
+
+
+def test_full_size_cavity_8192_properties(k64):
+    """config[3] at 8192^2, one timestep from a non-trivial state, checked against the oracle on
+    a 96-row band (the oracle needs minutes for the full 311 sweeps) and through global
+    properties: boundary conditions hold exactly on every wall, all values finite."""
+    if _free_host_gib() < 16:
+        pytest.skip("needs ~16 GiB of host memory")
+    n = 8192
+    mb, mp, mu, mv = W.cavity_masks(n, n)
+    dx = 2.0 / (n - 1)
+    cfg = W.Config(1.0, 0.1, 1e-4 * (100.0 / (n - 1)) ** 2, dx, dx)
+    gb, gp, gu, gv = (xgrid.Grid((n, n), float) for _ in range(4))
+    for gg, m in ((gb, mb), (gp, mp), (gu, mu), (gv, mv)):
+        gg.boundary[...] = m
+    for _ in range(2):
+        k64["cavity_kernel"](gb, gp, gu, gv, cfg)
+    u, v, p = gu.now, gv.now, gp.now
+    assert np.isfinite(u).all() and np.isfinite(v).all() and np.isfinite(p).all()
+    assert (u[-1, :] == 1.0).all() and (u[0, :] == 0.0).all() and (u[1:-1, 0] == 0.0).all()
+    assert (v[0, :] == 0.0).all() and (v[-1, :] == 0.0).all() and (v[:, 0] == 0.0).all()
+    assert (p[-1, :] == 0.0).all()                                   # p = 0 at y = 2
+    assert np.array_equal(p[1:-1, -1], p[1:-1, -2])                  # dp/dx = 0 at x = 2
+    assert np.array_equal(p[1:-1, 0], p[1:-1, 1])                    # dp/dx = 0 at x = 0
+    assert np.array_equal(p[0, 1:-1], p[1, 1:-1])                    # dp/dy = 0 at y = 0
+    assert np.abs(u[-2, 1:-1]).max() > 0.0                           # the lid drags the fluid
+
+
+def test_full_size_heat3d_slab(k64):
+    """config[4] slab 256x2048x2048: 2 steps vs the oracle, bit-exact (needs ~40 GiB host RAM)."""
+    if _free_host_gib() < 48:
+        pytest.skip("needs ~48 GiB of host memory")
+    shape = (256, 2048, 2048)
+    rng = np.random.default_rng(8)
+    ic = rng.random(shape)
+    mask = W.shell_mask(shape)
+    u, h = make_grid(ic, mask), HostGrid(shape)
+    h.now[...] = ic
+    h.boundary[...] = mask
+    del ic
+    for _ in range(2):
+        k64["heat_3d"](u, 0.1)
+        oracle.step_heat3d(h, 0.1)
+    eq(u._data[0], h._data[0], "L0")
+    eq(u._data[1], h._data[1], "L1")
