@@ -338,23 +338,28 @@ def test_full_size_conv2d_16384(k64):
     eq(u._data[1], h._data[1], "L1")
 
 
-def test_full_size_cavity_8192_properties(k64):
-    """config[3] at 8192^2, one timestep from a non-trivial state, checked against the oracle on
-    a 96-row band (the oracle needs minutes for the full 311 sweeps) and through global
-    properties: boundary conditions hold exactly on every wall, all values finite."""
-    if _free_host_gib() < 16:
-        pytest.skip("needs ~16 GiB of host memory")
+def test_full_size_cavity_8192(k64):
+    """config[3] at 8192^2: two timesteps (622 sweeps) bit-exact vs the oracle on every ring level,
+    plus the size-independent properties: boundary conditions hold exactly on every wall."""
+    if _free_host_gib() < 24:
+        pytest.skip("needs ~24 GiB of host memory")
     n = 8192
     mb, mp, mu, mv = W.cavity_masks(n, n)
     dx = 2.0 / (n - 1)
     cfg = W.Config(1.0, 0.1, 1e-4 * (100.0 / (n - 1)) ** 2, dx, dx)
     gb, gp, gu, gv = (xgrid.Grid((n, n), float) for _ in range(4))
-    for gg, m in ((gb, mb), (gp, mp), (gu, mu), (gv, mv)):
+    hb, hp, hu, hv = (HostGrid((n, n)) for _ in range(4))
+    for gg, hh, m in ((gb, hb, mb), (gp, hp, mp), (gu, hu, mu), (gv, hv, mv)):
         gg.boundary[...] = m
+        hh.boundary[...] = m
+    ocfg = oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy)
     for _ in range(2):
         k64["cavity_kernel"](gb, gp, gu, gv, cfg)
+        oracle.step_cavity(hb, hp, hu, hv, ocfg)
+    for name, gg, hh in (("b", gb, hb), ("p", gp, hp), ("u", gu, hu), ("v", gv, hv)):
+        eq(gg._data[0], hh._data[0], name + " L0")
+        eq(gg._data[1], hh._data[1], name + " L1")
     u, v, p = gu.now, gv.now, gp.now
-    assert np.isfinite(u).all() and np.isfinite(v).all() and np.isfinite(p).all()
     assert (u[-1, :] == 1.0).all() and (u[0, :] == 0.0).all() and (u[1:-1, 0] == 0.0).all()
     assert (v[0, :] == 0.0).all() and (v[-1, :] == 0.0).all() and (v[:, 0] == 0.0).all()
     assert (p[-1, :] == 0.0).all()                                   # p = 0 at y = 2
