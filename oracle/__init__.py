@@ -20,8 +20,10 @@ Parity pin: ``tests/golden/*.npz`` were produced by the *real* reference
 ``/root/reference`` exists) and ``tests/test_oracle.py`` checks this oracle
 against them bit-for-bit.  3-D and non-square 2-D cases cannot be produced by
 the reference (its linear index is wrong there); for those the
-oracle is additionally checked against an independent NumPy slice restatement
-(``oracle/numpy_ref.py``).
+oracle is additionally checked against independent NumPy slice restatements
+(tests/test_oracle.py).  ``oracle/interp.py`` is a second, generic oracle: a
+NumPy interpreter of arbitrary kernels, pinned against the same golden vectors
+(tests/test_interp.py) and used by the randomized differential tests.
 """
 from __future__ import annotations
 
@@ -97,7 +99,7 @@ class HostGrid:
         self.dtype = np.dtype(dtype)
         self.size = int(np.prod(self.shape, dtype=np.int64))
         stride0 = self.size // self.shape[0] if self.shape[0] else 1
-        self._pad = 2 * stride0 + 64
+        self._pad = 3 * stride0 + 64
         self._data = [self._zeros()]                      # :38
         self.boundary = np.zeros(self.shape, np.int32)    # :41
 

@@ -1,0 +1,81 @@
+"""Pin the generic NumPy interpreter (oracle/interp.py) against the golden vectors produced by
+the real reference, so that the randomized differential tests that use it as their oracle rest
+on something checked.  CPU only."""
+import numpy as np
+import pytest
+
+import xgrid_b200 as xgrid
+from xgrid_b200 import workloads as W
+from oracle import HostGrid
+from oracle.interp import Interp
+
+
+def eq(a, b):
+    assert a.dtype == b.dtype and a.shape == b.shape
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def host(arr, mask=None):
+    h = HostGrid(arr.shape, arr.dtype)
+    h.now[...] = arr
+    if mask is not None:
+        h.boundary[...] = mask
+    return h
+
+
+@pytest.fixture()
+def k64(tmp_path):
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    return W.make_kernels()
+
+
+@pytest.mark.parametrize("name,kernel", [
+    ("conv1d_f64", "convection_1d"), ("conv1d_stale_f64", "convection_1d"),
+    ("conv1d_nonlinear_f64", "convection_1d_nonlinear"), ("diff1d_f64", "diffusion_1d"),
+    ("conv2d_f64", "convection_2d"), ("diff2d_f64", "diffusion_2d"),
+])
+def test_single_grid(golden, k64, name, kernel):
+    g = golden(name)
+    u = host(g["u_in"], g["mask"])
+    run = Interp(k64[kernel])
+    for _ in range(int(g["steps"])):
+        run(u, *[float(x) for x in g["params"]])
+    eq(u._data[0], g["u.L0"])
+    eq(u._data[1], g["u.L1"])
+
+
+def test_cavity_41(golden, k64):
+    g = golden("cavity_41_f64")
+    b, p, u, v = (HostGrid((41, 41)) for _ in range(4))
+    b.boundary[...], p.boundary[...], u.boundary[...], v.boundary[...] = g["mb"], g["mp"], g["mu"], g["mv"]
+    cfg = W.Config(*[float(x) for x in g["cfg"]])
+    run = Interp(k64["cavity_kernel"])
+    for _ in range(int(g["steps"])):
+        run(b, p, u, v, cfg)
+    for tag, grid in (("b", b), ("p", p), ("u", u), ("v", v)):
+        eq(grid._data[0], g[f"{tag}.L0"])
+        eq(grid._data[1], g[f"{tag}.L1"])
+
+
+def test_ewmul_ring(golden, k64):
+    g = golden("ewmul_f64")
+    a, b, r = host(g["a_in"]), host(g["b_in"]), HostGrid((10000,))
+    run = Interp(k64["elementwise_mul"])
+    run(r, a, b)
+    run(r, a, b)
+    for tag, grid in (("r2", r), ("a2", a), ("b2", b)):
+        eq(grid._data[0], g[f"{tag}.L0"])
+        eq(grid._data[1], g[f"{tag}.L1"])
+
+
+def test_fp32_mixed_precision(golden, tmp_path):
+    xgrid.init(cacheroot=str(tmp_path))          # precision="float"
+    k = W.make_kernels()
+    for name, kern in (("diff1d_f32", "diffusion_1d"), ("conv2d_f32", "convection_2d")):
+        g = golden(name)
+        u = host(g["u_in"], g["mask"])
+        run = Interp(k[kern])
+        for _ in range(int(g["steps"])):
+            run(u, *[float(x) for x in g["params"]])
+        eq(u._data[0], g["u.L0"])
+        eq(u._data[1], g["u.L1"])

@@ -96,6 +96,9 @@ def tiled_geometry(shape, t: dict):
     return (gx, gy_mid, chunks), block, chunk0
 
 
+STATS: dict = {}          # kernel variant -> launches (diagnostics / tests)
+
+
 class Launcher:
     def __init__(self, program, grids: dict) -> None:
         self.program = program
@@ -192,6 +195,7 @@ class Launcher:
                 grid_dim, block_dim = dense_geometry(rows, cols, V)
             self.rt.launch(fn, grid_dim, block_dim, P, smem=smem)
             self.launches += 1
+            STATS[variant] = STATS.get(variant, 0) + 1
 
         written = [(self.grids[s.grid], s) for s in g.slots if s.written]
         edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)

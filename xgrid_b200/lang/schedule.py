@@ -590,6 +590,8 @@ class Program:
                 c, d = grid._spare_levels(2)
                 P.aux0, P.aux1, P.aux2, P.aux3 = x0.dev, x1.dev, c.dev, d.dev
                 rt.launch(fn, (blocks, 1, 1), (cfg["threads"], 1, 1), P, smem=cfg["smem"])
+                from .launch import STATS
+                STATS["multistep"] = STATS.get("multistep", 0) + 1
                 grid._ring, grid._spares = [c, d], [x0, x1]
                 c.where = d.where = "device"
                 c.halo_ok = d.halo_ok = False
