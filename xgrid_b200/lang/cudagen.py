@@ -834,29 +834,63 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
         L.append(f"#pragma unroll\n        for (int sv = 0; sv < NSV; ++sv) {{ fc_{m}[sv] = fl_{m}[sv]; "
                  f"if (o + 1 < iend) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv] + S0); }}")
     L.append("        xgb::pipe::mbar_wait(&full[tn % NS], (tn / NS) & 1);")
+    # stage base of every input plane this output plane reads (once per plane, not per tap)
+    dis = sorted({key[1] for key in windows})
+    for di in dis:
+        L.append(f"        const T *pl{di - c['DMIN']} = srow + (int64_t)((ps + {di - c['DMIN']} >= NS) ? "
+                 f"(ps + {di - c['DMIN']} - NS) : (ps + {di - c['DMIN']})) * (NREAD * RP * WP);")
+
+    def load_windows(ind: str) -> list:
+        out = []
+        for key, (lo, hi) in windows.items():
+            si, di, dj = key
+            out.append(f"{ind}T {wnames[key]}[V + {hi - lo}]; xgb::lds_window<T, V, {lo}, {hi}>("
+                       f"pl{di - c['DMIN']} + ({ridx[si]} * RP + ({dj})) * WP + kk[sv], {wnames[key]});")
+        return out
+
+    fast_body: list = []
+    slow_body: list = []
+    hoist: dict = {}
+    emit = ExprEmitter(module, _ident, tap, hoist)
+    fast_written = []
+    for a in g.stmts:
+        sw = a.sweep
+        sl = g.slot(sw.grid.name, "scratch" if g.implicit else sw.store.level)
+        if sw.mask == 0:
+            fast_body.append(f"                    o_{sl.field}[v] = {emit(a.value)};")
+            if sl not in fast_written:
+                fast_written.append(sl)
+    _emit_statements(g, module, tap, slow_body, "v", hoist)
     L.append("#pragma unroll")
     L.append("        for (int sv = 0; sv < NSV; ++sv) {")
-    for m in g.masks:
-        L.append(f"            int m_{m}[V];")
-        L.append(f"            if (act[sv]) xgb::ld_mask_flagged<V>(p.m_{m}, fc_{m}[sv], base[sv], m_{m}); else {{ for (int v = 0; v < V; ++v) m_{m}[v] = -1; }}")
-    for key, (lo, hi) in windows.items():
-        si, di, dj = key
-        L.append(f"            T {wnames[key]}[V + {hi - lo}];")
-        L.append(f"            {{ int q = ps + ({di} - DMIN); if (q >= NS) q -= NS;")
-        L.append(f"              xgb::lds_window<T, V, {lo}, {hi}>(srow + ((int64_t)(q * NREAD + {ridx[si]}) * RP + ({dj})) * WP + kk[sv], {wnames[key]}); }}")
-    for s_ in g.slots:
-        if s_.written:
-            L.append(f"            {module.ctype(s_.elem)} o_{s_.field}[V]; unsigned wr_{s_.field} = 0u;")
+    L.append("            if (act[sv]) {")
+    flags_zero = " && ".join(f"fc_{m}[sv] == 0" for m in g.masks) or "true"
+    L.append(f"                if ({flags_zero}) {{            // no boundary point in this 128-point chunk")
+    L.extend(load_windows("                    "))
+    for sl in fast_written:
+        L.append(f"                    {module.ctype(sl.elem)} o_{sl.field}[V];")
     L.append("#pragma unroll")
-    L.append("            for (int v = 0; v < V; ++v) {")
-    body: list = []
-    hoist: dict = {}
-    _emit_statements(g, module, tap, body, "v", hoist)
-    L.extend("        " + b for b in body)
-    L.append("            }")
+    L.append("                    for (int v = 0; v < V; ++v) {")
+    L.extend(fast_body)
+    L.append("                    }")
+    for sl in fast_written:
+        L.append(f"                    xgb::st_vec<{module.ctype(sl.elem)}, V>(p.{sl.field} + base[sv], o_{sl.field});")
+    L.append("                } else {")
+    for m in g.masks:
+        L.append(f"                    int m_{m}[V]; xgb::ld_mask_flagged<V>(p.m_{m}, fc_{m}[sv], base[sv], m_{m});")
+    L.extend(load_windows("                    "))
     for s_ in g.slots:
         if s_.written:
-            L.append(f"            if (act[sv]) xgb::st_pred<{module.ctype(s_.elem)}, V>(p.{s_.field} + base[sv], o_{s_.field}, wr_{s_.field});")
+            L.append(f"                    {module.ctype(s_.elem)} o_{s_.field}[V]; unsigned wr_{s_.field} = 0u;")
+    L.append("#pragma unroll")
+    L.append("                    for (int v = 0; v < V; ++v) {")
+    L.extend("            " + b for b in slow_body)
+    L.append("                    }")
+    for s_ in g.slots:
+        if s_.written:
+            L.append(f"                    xgb::st_pred<{module.ctype(s_.elem)}, V>(p.{s_.field} + base[sv], o_{s_.field}, wr_{s_.field});")
+    L.append("                }")
+    L.append("            }")
     L.append("            base[sv] += S0;")
     L.append("        }")
     L.append("        __syncwarp();")
