@@ -7,11 +7,11 @@ One JSON line on stdout (rank 0).  A *step* is one kernel call = one timestep
 of the workload (one pass of the hot path over the whole grid).
 
 Workloads (BASELINE.json configs):
-  conv1d   1-D linear convection, 2^24 points fp64 (config[1])  -- default at N=1
+  conv1d   1-D linear convection, 2^24 points fp64 per GPU (config[1]) -- default at every N
   conv1d_nl / diff1d   the other two config[1] kernels
   conv2d   2-D upwind convection 16384^2 fp64 (config[2]);  diff2d = 5-point variant
   cavity   lid-driven cavity 8192^2 fp64 (config[3]); value in Gpoint-updates/s, also timesteps/s
-  heat3d   3-D 7-point, 256x2048x2048 fp64 per GPU, slab-sharded (config[4]) -- default at N>1
+  heat3d   3-D 7-point, 256x2048x2048 fp64 per GPU, slab-sharded (config[4]); use --workload heat3d
   ewmul    README elementwise_mul, 10 000 points (config[0]; launch-latency bound)
 
 Metric: Gpoint-updates/s = grid points x interior (mask-0) statements per call x steps / time.
@@ -208,12 +208,32 @@ def run_ours(args, rank: int, world: int):
     rt = Runtime.get()
     if world > 1:
         # weak scaling: every rank owns a `shape` slab of the (world*shape[0], ...) global grid
-        if name != "heat3d":
-            raise SystemExit("multi-GPU bench is defined for the slab-sharded 3-D 7-point sweep (heat3d)")
         gshape = (shape[0] * world,) + tuple(shape[1:])
         lo, hi = rank * shape[0], (rank + 1) * shape[0]
-        rng = np.random.default_rng(rank)
-        inputs, scalars = [(rng.random(shape), W.shell_mask_slab(gshape, lo, hi))], (0.1,)
+        if name == "heat3d":
+            rng = np.random.default_rng(rank)
+            inputs, scalars = [(rng.random(shape), W.shell_mask_slab(gshape, lo, hi))], (0.1,)
+        elif name in ("conv1d", "conv1d_nl", "diff1d"):
+            n = gshape[0]
+            dx = 2.0 / (n - 1)
+            ic = np.ones(shape[0])
+            a, b = int(.5 / dx), int(1 / dx + 1)              # global IC of test.py:195-198, local slice
+            ic[max(a, lo) - lo:max(min(b, hi), lo) - lo] = 2.0
+            mask = np.zeros(shape[0], np.int32)
+            if rank == 0:
+                mask[0] = 1
+            if name == "conv1d":
+                scalars = (1.0, 0.5 * dx, dx)
+            elif name == "conv1d_nl":
+                scalars = (0.25 * dx, dx)
+            else:
+                if rank == world - 1:
+                    mask[-1] = 1
+                scalars = (0.01, 0.2 * dx * dx / 0.01, dx)
+            inputs = [(ic, mask)]
+        else:
+            raise SystemExit("multi-GPU bench is defined for the slab-sharded workloads: conv1d, conv1d_nl, "
+                             "diff1d (axis-0 = the only axis) and heat3d")
     else:
         gshape = shape
         inputs, scalars = build_inputs(name, shape, seed=rank)
@@ -359,7 +379,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload == "auto":
-        args.workload = "conv1d" if max(world, args.gpus) == 1 else "heat3d"
+        args.workload = "conv1d"        # BASELINE.json configs[1] at every N (sharded on its only axis)
     spec = WORKLOADS[args.workload]
 
     if args.impl == "reference":

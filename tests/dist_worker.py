@@ -107,6 +107,28 @@ def main():
             k["heat_3d"](u, a)
         ref = oracle_global(gshape, ic, mask, steps, a)
         ok = np.array_equal(u.now, ref.now[lo:hi]) and np.array_equal(u._data[1], ref._data[1][lo:hi])
+        # 1-D slabs through the deferred multi-step path (64 steps per launch + single-step remainder)
+        n1 = 3 * 40000 + 17
+        ic1, dx1 = W.ic_1d(n1)
+        ic1 = ic1 + 0.01 * np.random.default_rng(3).random(n1)
+        m1 = np.zeros(n1, np.int32)
+        m1[0] = m1[-1] = 1
+        m1[n1 // 2] = 1                      # a Dirichlet point right next to the slab boundary
+        m1[n1 // 2 + 3] = 7
+        u1 = xgrid.Grid((n1,), float)
+        lo1, hi1 = u1.row_range
+        u1.now[...] = ic1[lo1:hi1]
+        u1.boundary[...] = m1[lo1:hi1]
+        h1 = HostGrid((n1,))
+        h1.now[...] = ic1
+        h1.boundary[...] = m1
+        args1 = (0.01, 0.2 * dx1 * dx1 / 0.01, dx1)
+        for _ in range(150):
+            k["diffusion_1d"](u1, *args1)
+            oracle.step_diff1d(h1, *args1)
+        ok = ok and np.array_equal(u1.now, h1.now[lo1:hi1]) and np.array_equal(u1._data[1], h1._data[1][lo1:hi1])
+        from xgrid_b200.lang.launch import STATS
+        ok = ok and STATS.get("multistep", 0) >= 2
         t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:

@@ -129,30 +129,6 @@ XGB_DEV void ld_window(const T *row, T (&w)[V + HI - LO]) {
     for (int k = 0; k < HI; ++k) w[V - LO + k] = row[V + k];
 }
 
-// Same window, with the +-1 fringes taken from the neighbouring lanes' bodies
-// (warp shuffle) instead of extra loads.  Requires a full, converged warp whose
-// lanes own consecutive V-element bodies of the same row; lanes 0 / 31 fall
-// back to one scalar load each.
-template <class T, int V, int LO, int HI>
-XGB_DEV void ld_window_shfl(const T *row, T (&w)[V + HI - LO]) {
-    static_assert(LO >= -1 && HI <= 1, "shuffle window supports +-1 fringes");
-    T body[V];
-    ld_vec<T, V>(row, body);
-#pragma unroll
-    for (int i = 0; i < V; ++i) w[i - LO] = body[i];
-    const int lane = threadIdx.x & 31;
-    if constexpr (LO == -1) {
-        T left = __shfl_up_sync(0xffffffffu, body[V - 1], 1);
-        if (lane == 0) left = row[-1];
-        w[0] = left;
-    }
-    if constexpr (HI == 1) {
-        T right = __shfl_down_sync(0xffffffffu, body[0], 1);
-        if (lane == 31) right = row[V];
-        w[V - LO] = right;
-    }
-}
-
 // Window assembled from a register-resident body: w[k] = row[LO + k].  The
 // fringes come from the neighbouring lanes' bodies by warp shuffle; the lanes
 // on a warp edge (or at the end of a grid row) read them from global memory

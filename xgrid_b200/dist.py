@@ -158,6 +158,15 @@ class NcclTransport:
         self._next = (self._next + 1) % len(self._events)
         return self._events[self._next]
 
+    def exchange_bytes(self, data_ptr: int, data_bytes: int, halo_bytes: int, stream: int = 0) -> None:
+        """Halo exchange of a raw 1-D byte array laid out [halo | data | halo] (device masks)."""
+        d = self.shim.HaloDesc()
+        d.bytes = halo_bytes
+        d.lo_rank, d.hi_rank = self.topo.lo_rank, self.topo.hi_rank
+        d.send_lo, d.recv_lo = data_ptr, data_ptr - halo_bytes
+        d.send_hi, d.recv_hi = data_ptr + data_bytes - halo_bytes, data_ptr + data_bytes
+        self.shim.check(self.shim.lib().xgb_halo_exchange(self.shim.C.byref(d), 1, stream))
+
     def exchange(self, items: list, stream: int = 0) -> None:
         """items: [(grid, level, h)] -- refresh h ghost rows on both sides of each level."""
         if not items:

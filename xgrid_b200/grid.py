@@ -37,6 +37,7 @@ def _flush() -> None:
 
 SLACK = 64          # elements of linear slack before / after the padded array
 CHUNK = 128         # points per mask flag (XGB_CHUNK in xgb_stencil.cuh)
+MASK_GHOST = 64     # bytes of "outside" (255) mask on both sides of the device mask
 ALIGN = 256
 
 
@@ -95,6 +96,7 @@ class Grid:
         self._boundary = np.zeros(self.shape, dtype=np.int32)
         self._mask_touched = True
         self._mask_snapshot = None
+        self._mask_raw = 0
         self._mask_dev = 0
         self._flags_dev = 0
         self._mask_any = False
@@ -329,23 +331,33 @@ class Grid:
         self._mask_hist = None
         self._mask_version += 1
         flat = b.reshape(-1)
-        self._mask_any = bool(flat.any())
+        self._mask_any = bool(flat.any()) or self.sharded      # sharded: neighbours may carry masks
         if not self._mask_any:
             return                      # all-zero class: kernels get null mask pointers
         lo, hi = int(flat.min()), int(flat.max())
-        if lo < 0 or hi > 255:
-            self.logger.dead(f"boundary mask values must lie in [0, 255] on the B200 backend (got {lo}..{hi})")
+        if lo < 0 or hi > 254:
+            self.logger.dead(f"boundary mask values must lie in [0, 254] on the B200 backend (got {lo}..{hi})")
         m8 = flat.astype(np.uint8)
         nchunk = (self.size + CHUNK - 1) // CHUNK
-        padded = np.zeros(nchunk * CHUNK, np.uint8)
-        padded[:self.size] = m8
-        flags = padded.reshape(nchunk, CHUNK).any(axis=1).astype(np.uint8)
-        if not self._mask_dev:
-            self._mask_dev = rt.alloc(nchunk * CHUNK)
+        # device layout: [MASK_GHOST bytes of 255 | mask | padding to a whole chunk | MASK_GHOST x 255];
+        # 255 = "outside the grid" (never matches a statement); on a sharded 1-D grid the ghost bytes
+        # are replaced by the neighbours' edge masks
+        padded = np.full(MASK_GHOST + nchunk * CHUNK + MASK_GHOST, 255, np.uint8)
+        padded[MASK_GHOST:MASK_GHOST + self.size] = m8
+        padded[MASK_GHOST + self.size:MASK_GHOST + nchunk * CHUNK] = 0
+        body = padded[MASK_GHOST:MASK_GHOST + nchunk * CHUNK]
+        flags = body.reshape(nchunk, CHUNK).any(axis=1).astype(np.uint8)
+        if not self._mask_raw:
+            self._mask_raw = rt.alloc(padded.nbytes)
+            self._mask_dev = self._mask_raw + MASK_GHOST
             self._flags_dev = rt.alloc(nchunk)
-        rt.h2d(self._mask_dev, padded.ctypes.data, padded.nbytes)
+        rt.h2d(self._mask_raw, padded.ctypes.data, padded.nbytes)
         rt.h2d(self._flags_dev, flags.ctypes.data, flags.nbytes)
         rt.sync()
+        if self.sharded and self.dimension == 1:
+            from . import dist
+            # trailing ghost sits right after the last real byte on the neighbour's side
+            dist.transport().exchange_bytes(self._mask_dev, self.size, MASK_GHOST)
 
     def _mask_count(self, k: int) -> int:
         """Number of points whose boundary value is k (histogram cached per mask upload)."""
@@ -389,8 +401,8 @@ class Grid:
             for ptr, _ in self._lists.values():
                 if ptr:
                     rt.free(ptr)
-            if self._mask_dev:
-                rt.free(self._mask_dev)
+            if self._mask_raw:
+                rt.free(self._mask_raw)
                 rt.free(self._flags_dev)
         except Exception:
             pass

@@ -29,7 +29,9 @@ VARIANT_TILED = "tiled"
 VARIANT_MULTISTEP = "multistep"
 MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
 import os as _os
-MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "2"))   # rows loaded ahead of use per chain
+# rows loaded ahead of use per chain; 0 = off (measured: register prefetch costs occupancy, the
+# tiled variant prefetches through shared memory instead)
+MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "0"))
 
 
 @dataclass
@@ -346,6 +348,8 @@ def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims:
     add("const int64_t* __restrict__", "list", ctypes.c_void_p)
     add("int64_t", "count", ctypes.c_int64)
     add("int64_t", "chunk0", ctypes.c_int64)     # axis-0 points per CTA in the marching variant
+    add("int64_t", "open_lo", ctypes.c_int64)    # slab has a neighbour below / above: its ghost points
+    add("int64_t", "open_hi", ctypes.c_int64)    # are real grid points (multi-step variant)
     add("int64_t", "r_lo", ctypes.c_int64)       # axis-0 range [r_lo, r_hi) swept by this launch
     add("int64_t", "r_hi", ctypes.c_int64)       # (march / tiled variants; edge-first launches of a slab)
     add("int64_t", "rows", ctypes.c_int64)
@@ -690,6 +694,8 @@ def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
 # --------------------------------------------------------------------------- tiled (async pipeline) variant
 TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", str(56 * 1024)))
 TILED_TJ = int(_os.environ.get("XGB_TJ", "8"))
+TILED_WX3 = int(_os.environ.get("XGB_WX3", "1"))       # consumer warps side by side along k in 3-D
+TILED_NSV = int(_os.environ.get("XGB_NSV", "2"))
 
 
 def tiled_config(g: Group):
@@ -702,7 +708,7 @@ def tiled_config(g: Group):
     if esize not in (4, 8):
         return None
     V = 16 // esize
-    NSV = 2
+    NSV = TILED_NSV
     dmin = dmax = hj = hk = 0
     for a in g.stmts:
         for ld in a.sweep.loads:
@@ -715,7 +721,7 @@ def tiled_config(g: Group):
     if g.ndim == 2:
         ncw, tj, wx = 8, 1, 8                  # 8 consumer warps side by side
     else:
-        tj, wx = TILED_TJ, 1                   # one warp per j-row
+        tj, wx = TILED_TJ, TILED_WX3           # tj rows x wx warps per row
         ncw = tj * wx
     W = wx * 32 * V * NSV
     wp, rp = W + 2 * hk, tj + 2 * hj
@@ -984,7 +990,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("    for (int q = threadIdx.x; q < L; q += NT) {")
     L.append("        const int64_t gi = g0 + q;")
     L.append(f"        int m = 255;                                  // outside the grid: never updated")
-    L.append(f"        if (gi >= 0 && gi < p.n0) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
+    L.append(f"        if ((gi >= 0 || p.open_lo) && (gi < p.n0 || p.open_hi)) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
     L.append("        sm[q] = (uint8_t)m; any |= m;")
     L.append("    }")
     L.append("    const int masked = __syncthreads_or(any);")

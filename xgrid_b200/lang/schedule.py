@@ -462,8 +462,7 @@ class Program:
         if self.batchable and self.config.temporal:
             # defer: a run of identical calls is executed T steps per launch on flush
             grid = args[self._grid_pos]
-            if (getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and not grid.sharded
-                    and grid.dimension == 1):
+            if getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and grid.dimension == 1:
                 key = tuple(a for n, a in enumerate(args) if n != self._grid_pos)
                 p = _PENDING
                 if p is not None and p["program"] is self and p["grid"] is grid and p["key"] == key \
@@ -572,7 +571,8 @@ class Program:
             env = captured[0]
             rt = self._runtime()
             grid._extend_time(2)
-            grid._prepare_device(1)
+            # a slab needs the neighbours' next H points of BOTH ring levels (and of the mask)
+            grid._prepare_device(cfg["H"] if grid.sharded else 1)
             fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_MULTISTEP, 1), cfg["smem"])
             P = g.params_cls()
             P.n0 = grid.shape[0]
@@ -585,8 +585,16 @@ class Program:
             for name, t in g.scalars.items():
                 setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
             blocks = (grid.shape[0] + cfg["W"] - 1) // cfg["W"]
+            if grid.sharded:
+                from .. import dist
+                topo = dist.topology()
+                P.open_lo, P.open_hi = int(topo.lo_rank >= 0), int(topo.hi_rank >= 0)
             while count - done >= T:
                 x0, x1 = grid._ring[0], grid._ring[1]
+                if grid.sharded:
+                    stale = [(grid, lv, cfg["H"]) for lv in (x0, x1) if not lv.halo_ok]
+                    if stale:
+                        dist.transport().exchange(stale)
                 c, d = grid._spare_levels(2)
                 P.aux0, P.aux1, P.aux2, P.aux3 = x0.dev, x1.dev, c.dev, d.dev
                 rt.launch(fn, (blocks, 1, 1), (cfg["threads"], 1, 1), P, smem=cfg["smem"])
