@@ -911,7 +911,8 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
 
 # --------------------------------------------------------------------------- multi-step (temporal blocking) variant
 MULTISTEP_T = int(_os.environ.get("XGB_MS_T", "64"))
-MULTISTEP_W = int(_os.environ.get("XGB_MS_W", "4096"))
+MULTISTEP_S = int(_os.environ.get("XGB_MS_S", "4"))      # register sub-steps per shared-memory round trip
+MULTISTEP_P = int(_os.environ.get("XGB_MS_P", "8"))      # points per thread in the register path
 
 
 def multistep_config(g: Group):
@@ -932,79 +933,126 @@ def multistep_config(g: Group):
     T = MULTISTEP_T
     while T * h > 64:                 # halo must stay inside the level's zero slack
         T //= 2
-    T -= T % 2                        # even: the ring order after T ticks equals the order before
+    S = MULTISTEP_S                   # time steps advanced in registers per shared-memory round trip
+    T -= T % (2 * S) if T >= 2 * S else T % 2
     if T < 4:
         return None
-    W, H = MULTISTEP_W, T * h
-    L = W + 2 * H
-    return {"T": T, "W": W, "H": H, "h": h, "L": L, "threads": 512, "V": 16 // elem.width_bytes,
-            "smem": 2 * L * elem.width_bytes + L + 64}
+    if T % S or S % 2:
+        S = 2
+    if (S * h) % (16 // elem.width_bytes):
+        return None                   # register windows must start on a 16-byte boundary
+    NT, P = 512, MULTISTEP_P
+    H = T * h
+    L = NT * P                        # window = one P-point body per thread
+    if L <= 4 * H:
+        return None
+    W = L - 2 * H
+    PAD = S * h + (-(S * h)) % (16 // elem.width_bytes)      # keeps bodies 16-byte aligned
+    V = 16 // elem.width_bytes
+    if P & (P - 1) or P % V:
+        return None
+    swlen, marg = L + (L // P) * V, 2 * PAD + 2 * V
+    return {"T": T, "S": S, "P": P, "W": W, "H": H, "h": h, "L": L, "PAD": PAD, "threads": NT, "V": V,
+            "smem": 2 * (swlen + 2 * marg) * elem.width_bytes + L + 64}
 
 
 def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     """T steps per launch.  Two shared-memory buffers start as copies of the two ring levels
-    (now / previous) of a W+2H window; every step writes the *older* buffer where a statement's
-    mask matches -- exactly what T ticks + T sweeps do to the ring (unwritten points keep the value
-    from two steps back) -- and the window of valid points shrinks by h per step."""
+    (now / previous) of an L = W+2H window; every step writes the *older* buffer where a
+    statement's mask matches -- exactly what T ticks + T sweeps do to the ring (unwritten points
+    keep the value from two steps back) -- and the window of valid points shrinks by
+    h per step.  Tiles without boundary points take the register path: each thread loads its P
+    points plus an S*h fringe, advances S steps in registers and writes back the last two.
+    Shared memory is laid out with one 16-byte pad per P-point body (XSW) so that the 128-bit
+    accesses of consecutive threads fall on different banks."""
     elem = g.slots[0].elem
     T_ = module.ctype(elem)
     gname = g.slots[0].grid
+    S, P, h, V = c["S"], c["P"], c["h"], c["V"]
+    psh = P.bit_length() - 1
 
-    def tap(e: ir.Stencil) -> str:
-        return f"cur[q + ({e.space_offset[-1]})]"
-
-    def stmts(masked: bool, hoist: dict) -> list:
-        emit = ExprEmitter(module, _ident, tap, hoist)
-        out = []
-        for a in g.stmts:
-            rhs = emit(a.value)
-            if masked:
-                out.append(f"if (m == {a.sweep.mask}) nxt[q] = {rhs};")
-            elif a.sweep.mask == 0:
-                out.append(f"nxt[q] = {rhs};")
-        return out
+    def slow_tap(e: ir.Stencil) -> str:
+        return f"cur[XSW(q + ({e.space_offset[-1]}))]"
 
     hoist: dict = {}
-    fast, slow = stmts(False, hoist), stmts(True, hoist)
+    slow_emit = ExprEmitter(module, _ident, slow_tap, hoist)
+    slow = [f"if (m == {a.sweep.mask}) nxt[XSW(q)] = {slow_emit(a.value)};" for a in g.stmts]
+    mask0 = [a for a in g.stmts if a.sweep.mask == 0]
+
+    # register path: level s (1..S) holds N0 - 2*s*h values; x{s}[i] is point (first - (S-s)*h + i)
+    N0 = P + 2 * S * h
+    reg_lines = []
+    for s_ in range(1, S + 1):
+        n_out = N0 - 2 * s_ * h
+        reg_lines.append(f"            E x{s_}[{n_out}];")
+        reg_lines.append("#pragma unroll")
+        reg_lines.append(f"            for (int i = 0; i < {n_out}; ++i) {{")
+
+        def reg_tap(e: ir.Stencil, lvl=s_ - 1) -> str:
+            return f"x{lvl}[i + ({h + e.space_offset[-1]})]"
+
+        emit = ExprEmitter(module, _ident, reg_tap, hoist)
+        if mask0:
+            reg_lines.append(f"                x{s_}[i] = {emit(mask0[-1].value)};")
+        else:
+            reg_lines.append(f"                x{s_}[i] = x{s_ - 1}[i + {h}];")
+        reg_lines.append("            }")
+
     name = kernel_name(g, VARIANT_MULTISTEP, 1)
     L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
-    L.append(f"    constexpr int T = {c['T']}, HS = {c['h']}, H = {c['H']}, W = {c['W']}, L = {c['L']}, NT = {c['threads']}, V = {c['V']};")
+    L.append(f"    constexpr int T = {c['T']}, S = {S}, P = {P}, PSH = {psh}, HS = {h}, H = {c['H']}, W = {c['W']}, L = {c['L']}, "
+             f"PAD = {c['PAD']}, NT = {c['threads']}, V = {V};")
+    L.append("    #define XSW(i) ((i) + (((i) >> PSH) * V))          /* one V-element pad per P-point body */")
+    L.append("    constexpr int MARG = 2 * PAD + 2 * V, SWLEN = L + (L >> PSH) * V;")
     L.append(f"    typedef {T_} E;")
     L.extend(hoist_lines(hoist))
     L.append("    extern __shared__ __align__(16) unsigned char xgb_smem[];")
-    L.append("    E *b0 = reinterpret_cast<E *>(xgb_smem);      // starts as the current level  (u^n)")
-    L.append("    E *b1 = b0 + L;                               // starts as the previous level (u^{n-1})")
-    L.append("    uint8_t *sm = reinterpret_cast<uint8_t *>(b1 + L);")
+    L.append("    E *b0 = reinterpret_cast<E *>(xgb_smem) + MARG;      // starts as the current level  (u^n)")
+    L.append("    E *b1 = b0 + SWLEN + 2 * MARG;                       // starts as the previous level (u^{n-1})")
+    L.append("    uint8_t *sm = reinterpret_cast<uint8_t *>(b1 + SWLEN + MARG);")
     L.append("    const E *now = static_cast<const E *>(p.aux0), *prev = static_cast<const E *>(p.aux1);")
     L.append("    E *out0 = static_cast<E *>(p.aux2), *out1 = static_cast<E *>(p.aux3);")
     L.append("    const int64_t g0 = (int64_t)blockIdx.x * W - H;   // global index of window element 0")
+    L.append("    if (threadIdx.x < 2 * PAD) {                       // fringes outside the window: never valid, keep finite")
+    L.append("        const int k = threadIdx.x < PAD ? (int)threadIdx.x - PAD : L + (int)threadIdx.x - PAD;")
+    L.append("        b0[XSW(k)] = E(0); b1[XSW(k)] = E(0);")
+    L.append("    }")
     L.append("    for (int q = threadIdx.x * V; q < L; q += NT * V) {")
     L.append("        E a[V], b[V];")
     L.append("        const int64_t gi = g0 + q;                 // stay inside the level's zero slack")
     L.append("        if (gi >= -64 && gi + V <= p.n0 + 64) { xgb::ld_vec<E, V>(now + gi, a); xgb::ld_vec<E, V>(prev + gi, b); }")
     L.append("        else { for (int v = 0; v < V; ++v) { a[v] = E(0); b[v] = E(0); } }")
-    L.append("#pragma unroll")
-    L.append("        for (int v = 0; v < V; ++v) { b0[q + v] = a[v]; b1[q + v] = b[v]; }")
+    L.append("        xgb::st_vec<E, V>(b0 + XSW(q), a); xgb::st_vec<E, V>(b1 + XSW(q), b);")
     L.append("    }")
     L.append("    int any = 0;")
     L.append("    for (int q = threadIdx.x; q < L; q += NT) {")
     L.append("        const int64_t gi = g0 + q;")
-    L.append(f"        int m = 255;                                  // outside the grid: never updated")
+    L.append("        int m = 255;                                  // outside the grid: never updated")
     L.append(f"        if ((gi >= 0 || p.open_lo) && (gi < p.n0 || p.open_hi)) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
     L.append("        sm[q] = (uint8_t)m; any |= m;")
     L.append("    }")
     L.append("    const int masked = __syncthreads_or(any);")
-    L.append("    E *cur = b0, *nxt = b1;")
     L.append("    if (!masked) {")
-    L.append("        for (int s = 1; s <= T; ++s) {")
-    L.append("#pragma unroll 4")
-    L.append("            for (int q = s * HS + threadIdx.x; q < L - s * HS; q += NT) {")
-    L.extend("                " + x for x in fast)
+    L.append("        // register path: S steps per round; b0 always receives the newest level (S is even)")
+    L.append("        const int first = threadIdx.x * P;")
+    L.append("        for (int round = 0; round < T / S; ++round) {")
+    L.append(f"            E x0[{N0}];")
+    L.append("#pragma unroll")
+    L.append(f"            for (int i = 0; i < {N0}; i += V) xgb::ld_vec<E, V>(b0 + XSW(first - S * HS + i), *reinterpret_cast<E (*)[V]>(&x0[i]));")
+    L.extend(reg_lines)
+    L.append("            __syncthreads();                          // everyone has read b0 before it is overwritten")
+    L.append("#pragma unroll")
+    L.append(f"            for (int i = 0; i < P; i += V) {{")
+    L.append(f"                E lo_[V], hi_[V];")
+    L.append("#pragma unroll")
+    L.append(f"                for (int v = 0; v < V; ++v) {{ hi_[v] = x{S}[i + v]; lo_[v] = x{S - 1}[i + v + HS]; }}")
+    L.append(f"                xgb::st_vec<E, V>(b0 + XSW(first + i), hi_);")
+    L.append(f"                xgb::st_vec<E, V>(b1 + XSW(first + i), lo_);")
     L.append("            }")
     L.append("            __syncthreads();")
-    L.append("            E *t = cur; cur = nxt; nxt = t;")
     L.append("        }")
     L.append("    } else {")
+    L.append("        E *cur = b0, *nxt = b1;")
     L.append("        for (int s = 1; s <= T; ++s) {")
     L.append("            for (int q = s * HS + threadIdx.x; q < L - s * HS; q += NT) {")
     L.append("                const int m = sm[q];")
@@ -1017,14 +1065,14 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("    // T is even: b0 holds u^{n+T}, b1 holds u^{n+T-1}")
     L.append("    for (int q = H + threadIdx.x * V; q < H + W; q += NT * V) {")
     L.append("        const int64_t gi = g0 + q;")
+    L.append("        E a[V], b[V];")
+    L.append("        xgb::ld_vec<E, V>(b0 + XSW(q), a); xgb::ld_vec<E, V>(b1 + XSW(q), b);")
     L.append("        if (gi + V <= p.n0) {")
-    L.append("            E a[V], b[V];")
-    L.append("#pragma unroll")
-    L.append("            for (int v = 0; v < V; ++v) { a[v] = b0[q + v]; b[v] = b1[q + v]; }")
     L.append("            xgb::st_vec<E, V>(out0 + gi, a); xgb::st_vec<E, V>(out1 + gi, b);")
     L.append("        } else {")
-    L.append("            for (int v = 0; v < V; ++v) if (gi + v < p.n0) { out0[gi + v] = b0[q + v]; out1[gi + v] = b1[q + v]; }")
+    L.append("            for (int v = 0; v < V; ++v) if (gi + v < p.n0) { out0[gi + v] = a[v]; out1[gi + v] = b[v]; }")
     L.append("        }")
     L.append("    }")
+    L.append("    #undef XSW")
     L.append("}")
     return "\n".join(L) + "\n"
