@@ -313,7 +313,7 @@ def run_ours(args, rank: int, world: int):
         offload = {"value": points * spec["stmts"] * Ko / dt / 1e9, "unit": "Gpoint-updates/s",
                    "h2d_bytes_per_step": float(sum(o.nbytes for o in outs)),
                    "d2h_bytes_per_step": float(sum(o.nbytes for o in outs)), "steps": Ko,
-                   "note": "every step: H2D full state, one kernel call, D2H full state (pageable NumPy mirrors)"}
+                   "note": "every step: H2D full state, one kernel call, D2H full state (page-locked NumPy mirrors)"}
         del g2, outs
 
     if rank != 0:
