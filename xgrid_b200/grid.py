@@ -49,7 +49,7 @@ def parse_numpy_dtype(t: Value):
 
 class _Level:
     """One time level: device allocation + optional host mirror."""
-    __slots__ = ("dev", "host", "where", "raw", "halo_ok", "halo_event", "pinned")
+    __slots__ = ("dev", "host", "where", "raw", "halo_ok", "halo_event", "pinned", "xfers")
 
     def __init__(self, host=None) -> None:
         self.dev = 0            # device pointer of the first *real* element (0 = not allocated)
@@ -59,6 +59,7 @@ class _Level:
         self.halo_ok = False    # ghost rows hold the neighbours' current rows (sharded grids)
         self.pinned = 0         # address of the page-locked host mirror (0 = pageable)
         self.halo_event = 0     # event of a halo exchange still in flight on the comm stream
+        self.xfers = 0          # address of the mirror that has been transferred once (pin on 2nd use)
 
 
 class Grid:
@@ -202,11 +203,16 @@ class Grid:
     PIN_MIN_BYTES = 1 << 20
 
     def _pin(self, lv: _Level) -> None:
-        """Page-lock a host mirror once so H2D / D2H run at full PCIe speed."""
+        """Page-lock a host mirror so H2D / D2H run at full PCIe speed -- from its SECOND
+        transfer on: registering costs about as much as one pageable copy, so one-shot
+        uploads (initial conditions) and downloads (final result) stay pageable."""
         if lv.host is None or lv.host.nbytes < self.PIN_MIN_BYTES:
             return
         addr = lv.host.ctypes.data
         if lv.pinned == addr:
+            return
+        if lv.xfers != addr:            # first transfer of this buffer: remember it, do not pin yet
+            lv.xfers = addr
             return
         self._unpin(lv)
         from .runtime import shim
@@ -331,29 +337,26 @@ class Grid:
         self._mask_hist = None
         self._mask_version += 1
         flat = b.reshape(-1)
-        self._mask_any = bool(flat.any()) or self.sharded      # sharded: neighbours may carry masks
-        if not self._mask_any:
-            return                      # all-zero class: kernels get null mask pointers
-        lo, hi = int(flat.min()), int(flat.max())
-        if lo < 0 or hi > 254:
-            self.logger.dead(f"boundary mask values must lie in [0, 254] on the B200 backend (got {lo}..{hi})")
-        m8 = flat.astype(np.uint8)
         nchunk = (self.size + CHUNK - 1) // CHUNK
-        # device layout: [MASK_GHOST bytes of 255 | mask | padding to a whole chunk | MASK_GHOST x 255];
+        if not flat.any() and not self.sharded:
+            self._mask_any = False      # all-zero class: kernels get null mask pointers
+            return
+        self._mask_any = True
+        # device layout: [MASK_GHOST bytes of 255 | mask | zero padding to a whole chunk | MASK_GHOST x 255];
         # 255 = "outside the grid" (never matches a statement); on a sharded 1-D grid the ghost bytes
         # are replaced by the neighbours' edge masks
-        padded = np.full(MASK_GHOST + nchunk * CHUNK + MASK_GHOST, 255, np.uint8)
-        padded[MASK_GHOST:MASK_GHOST + self.size] = m8
-        padded[MASK_GHOST + self.size:MASK_GHOST + nchunk * CHUNK] = 0
-        body = padded[MASK_GHOST:MASK_GHOST + nchunk * CHUNK]
-        flags = body.reshape(nchunk, CHUNK).any(axis=1).astype(np.uint8)
         if not self._mask_raw:
-            self._mask_raw = rt.alloc(padded.nbytes)
+            self._mask_raw = rt.alloc(MASK_GHOST + nchunk * CHUNK + MASK_GHOST)
             self._mask_dev = self._mask_raw + MASK_GHOST
             self._flags_dev = rt.alloc(nchunk)
-        rt.h2d(self._mask_raw, padded.ctypes.data, padded.nbytes)
-        rt.h2d(self._flags_dev, flags.ctypes.data, flags.nbytes)
-        rt.sync()
+            rt.memset(self._mask_raw, 255, MASK_GHOST)
+            rt.memset(self._mask_dev + nchunk * CHUNK, 255, MASK_GHOST)
+        from .runtime.devmask import compile_mask
+        hist, bad = compile_mask(rt, np.ascontiguousarray(b, np.int32), self._mask_dev, self._flags_dev,
+                                 nchunk * CHUNK)
+        if bad:
+            self.logger.dead("boundary mask values must lie in [0, 254] on the B200 backend")
+        self._mask_hist = hist
         if self.sharded and self.dimension == 1:
             from . import dist
             # trailing ghost sits right after the last real byte on the neighbour's side
