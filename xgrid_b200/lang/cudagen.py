@@ -172,8 +172,9 @@ class ModuleBuilder:
     """Accumulates one CUDA translation unit: struct definitions, ``__device__``
     helpers for called operators, and one or more sweep kernels."""
 
-    def __init__(self, overstep: str = "none") -> None:
+    def __init__(self, overstep: str = "none", comment: bool = False) -> None:
         self.overstep = overstep
+        self.comment = comment
         self.structs: dict[str, str] = {}
         self.functions: dict[str, str] = {}
         self.kernels: list[str] = []
@@ -434,6 +435,10 @@ def _emit_statements(g: Group, module: ModuleBuilder, tap, lines: list, vexpr: s
         store_level = "scratch" if g.implicit else sw.store.level
         s = g.slot(sw.grid.name, store_level)
         rhs = emit(a.value)
+        if module.comment:
+            # init(comment=True): map device code back to the user's Python source
+            # (xgrid/lang/generator.py:242-244 emits the same #line directives into its C)
+            lines.append(f'#line {a.location.line} "{a.location.file}"')
         lines.append(f"        if (m_{sw.grid.name}[{vexpr}] == {sw.mask}) {{ "
                      f"o_{s.field}[{vexpr}] = {rhs}; wr_{s.field} |= 1u << {vexpr}; }}")
         if g.implicit:

@@ -384,7 +384,7 @@ class Program:
         self.grid_ndims = {n: t.dimension for n, t in self.grid_args}
         Program._serial += 1
         tag = "".join(ch if ch.isalnum() else "_" for ch in op.name)
-        self.module_builder = cudagen.ModuleBuilder(self.config.overstep)
+        self.module_builder = cudagen.ModuleBuilder(self.config.overstep, self.config.comment)
         scope_types = {n: v.type for n, v in self.ir.scope.items()}
         for g in self.groups:
             g.name = f"xg_{tag}_g{g.gid}"

@@ -1,10 +1,10 @@
 """Leveled logger for the B200 backend.
 
-Mirrors the observable behaviour of the reference logger
-(xgrid/util/logging.py:22-60): class-level ``stdouts`` / ``stderrs`` /
-``level`` that callers may replace, and ``dead()`` which logs and then raises
-a plain ``Exception`` carrying the message tuple.  Cosmetics (colours) are
-intentionally minimal; SURVEY.md §2 row 11 marks them out of scope.
+Keeps the observable contract of the reference logger (xgrid/util/logging.py:22-60) that user
+code and tests rely on: class-level ``stdouts`` / ``stderrs`` sinks and ``level`` threshold that
+callers may replace, one method per level, and ``dead()`` which logs and then raises a plain
+``Exception`` carrying the message tuple.  Colours and console classes are out of scope
+(SURVEY.md §2 row 11).
 """
 from __future__ import annotations
 
@@ -21,6 +21,15 @@ class LogLevel(IntEnum):
     dead = 4
 
 
+def _write(sink, text: str) -> None:
+    """Sinks are file-like objects or reference-style consoles with ``println``."""
+    println = getattr(sink, "println", None)
+    if println is not None:
+        println(text)
+    else:
+        sink.write(text + "\n")
+
+
 class Logger:
     stdouts: list = [sys.stdout]
     stderrs: list = [sys.stderr]
@@ -32,29 +41,24 @@ class Logger:
     def log(self, level: LogLevel, *msg: str) -> None:
         if int(level) < int(Logger.level):
             return
-        sinks = Logger.stdouts if level <= LogLevel.done else Logger.stderrs
-        for sink in sinks:
-            for n, line in enumerate(msg):
-                text = f"[ {level.name} | {self.name} ] {line}" if n == 0 else str(line)
-                write = getattr(sink, "println", None)
-                if write is not None:
-                    write(text)
-                else:
-                    sink.write(text + "\n")
-
-    def info(self, *msg: str) -> None:
-        self.log(LogLevel.info, *msg)
-
-    def done(self, *msg: str) -> None:
-        self.log(LogLevel.done, *msg)
-
-    def warn(self, *msg: str) -> None:
-        self.log(LogLevel.warn, *msg)
-
-    def fail(self, *msg: str) -> None:
-        self.log(LogLevel.fail, *msg)
+        head, *rest = msg or ("",)
+        lines = [f"[ {level.name} | {self.name} ] {head}", *map(str, rest)]
+        for sink in (Logger.stdouts if level <= LogLevel.done else Logger.stderrs):
+            for line in lines:
+                _write(sink, line)
 
     def dead(self, *msg: str) -> NoReturn:
-        # xgrid/util/logging.py:58-60 -- log, then raise Exception(msg tuple)
+        # xgrid/util/logging.py:58-60 -- report, then raise Exception(message tuple)
         self.log(LogLevel.dead, *msg)
         raise Exception(msg)
+
+
+def _leveled(level: LogLevel):
+    def emit(self, *msg: str) -> None:
+        self.log(level, *msg)
+    emit.__name__ = level.name
+    return emit
+
+
+for _lv in (LogLevel.info, LogLevel.done, LogLevel.warn, LogLevel.fail):
+    setattr(Logger, _lv.name, _leveled(_lv))
