@@ -78,7 +78,14 @@ def gen_source(seed: int, ndim: int, ngrids: int, single_1d: bool = False) -> st
             lines.append(f"    for _ in range(0, {int(rng.integers(2, 4))}):")
             in_loop = True
             ind = "        "
-        if rng.random() < 0.55:
+        r2 = rng.random()
+        if r2 < 0.12:
+            # scalar control flow decides which sweep runs (host side)
+            lines.append(f"{ind}if a * b > {round(float(rng.uniform(0.2, 0.8)), 2)}:")
+            lines.append(f"{ind}    {tgt}[{zero}] = {_expr(rng, grids, ndim, None, max_level)}")
+            lines.append(f"{ind}else:")
+            lines.append(f"{ind}    {tgt}[{zero}] = {_expr(rng, grids, ndim, None, max_level)}")
+        elif r2 < 0.6:
             lines.append(f"{ind}{tgt}[{zero}] = {_expr(rng, grids, ndim, None, max_level)}")
         else:
             k = int(rng.integers(1, 4))

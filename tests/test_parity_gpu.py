@@ -386,3 +386,75 @@ def test_full_size_heat3d_slab(k64):
         oracle.step_heat3d(h, 0.1)
     eq(u._data[0], h._data[0], "L0")
     eq(u._data[1], h._data[1], "L1")
+
+
+# --------------------------------------------------------------------------- less common DSL features
+from dataclasses import dataclass as _dataclass
+
+
+@_dataclass
+class Vec2:
+    x: float
+    y: float
+
+
+def test_struct_element_grid(tmp_path):
+    """Grids of by-value structs (record dtype host mirror, xgrid/xgrid/__init__.py:10-18):
+    field loads through `g[off].field`, whole-struct stores through the constructor."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    v1 = xgrid.grid[Vec2, 1]
+
+    @xgrid.kernel()
+    def rotate(p: v1, a: float) -> None:
+        p[0] = Vec2(p[0].x + a * p[-1].y, p[0].y - a * p[1].x)
+        with xgrid.boundary(1):
+            p[0] = Vec2(0.0, 1.0)
+
+    n = 1000
+    rng = np.random.default_rng(2)
+    g = xgrid.Grid((n,), Vec2)
+    x0, y0 = rng.random(n), rng.random(n)
+    g.now["x"] = x0
+    g.now["y"] = y0
+    g.boundary[0] = g.boundary[-1] = 1
+    x, y = x0.copy(), y0.copy()
+    for _ in range(3):
+        rotate(g, 0.25)
+        nx, ny = x.copy(), y.copy()
+        nx[1:-1] = x[1:-1] + 0.25 * y[:-2]
+        ny[1:-1] = y[1:-1] - 0.25 * x[2:]
+        nx[0] = nx[-1] = 0.0
+        ny[0] = ny[-1] = 1.0
+        x, y = nx, ny
+    assert np.array_equal(g.now["x"], x) and np.array_equal(g.now["y"], y)
+
+
+def test_scalar_control_flow_around_sweeps(k64, tmp_path):
+    """`if` / `while` on scalars decide which sweeps run (host control flow, generator.py:264-280)."""
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def stepper(u: f1, n: int, a: float) -> None:
+        i = 0
+        while i < n:
+            if i % 2 == 0:
+                u[0] = u[0][0] + a * (u[1][0] - u[-1][0])
+            else:
+                u[0] = u[0][0] - a
+            i += 1
+        with xgrid.boundary(1):
+            u[0] = 0.5
+
+    n = 5000
+    ic = np.random.default_rng(9).random(n)
+    u = make_grid(ic)
+    u.boundary[0] = u.boundary[-1] = 1
+    h = HostGrid((n,))
+    h.now[...] = ic
+    h.boundary[0] = h.boundary[-1] = 1
+    from oracle.interp import Interp
+    ref = Interp(stepper)
+    for calls in range(3):
+        stepper(u, 3 + calls, 0.1)
+        ref(h, 3 + calls, 0.1)
+    eq(u._data[0], h._data[0])
