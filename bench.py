@@ -288,6 +288,7 @@ def run_ours(args, rank: int, world: int):
     # ---- end to end through the public API (`e2e`): host IC -> K steps -> host result ----
     e2e = None
     offload = None
+    probe_leg = None
     if world == 1 and not args.no_e2e:
         Ke = K
         t0 = time.perf_counter()
@@ -314,6 +315,19 @@ def run_ours(args, rank: int, world: int):
                    "h2d_bytes_per_step": float(sum(o.nbytes for o in outs)),
                    "d2h_bytes_per_step": float(sum(o.nbytes for o in outs)), "steps": Ko,
                    "note": "every step: H2D full state, one kernel call, D2H full state (page-locked NumPy mirrors)"}
+        # strict per-step read-back: every step's result is observed on the host through element
+        # indexing (forces one launch + one device->host read per step; no deferral, no batching)
+        Kp = max(3, min(1000, K))
+        probe = tuple(n // 2 for n in shape)
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(Kp):
+            kern(*g2, *scalars)
+            acc += float(g2[0][probe])
+        dt = time.perf_counter() - t0
+        probe_leg = {"value": points * spec["stmts"] * Kp / dt / 1e9, "unit": "Gpoint-updates/s",
+                     "h2d_bytes_per_step": 8.0 * len(scalars), "d2h_bytes_per_step": 8.0, "steps": Kp,
+                     "note": "every step: one kernel call, then one element of the result read on the host"}
         del g2, outs
 
     if rank != 0:
@@ -360,6 +374,7 @@ def run_ours(args, rank: int, world: int):
     if e2e is not None:
         line["e2e"] = e2e
         line["e2e_offload"] = offload
+        line["e2e_probe"] = probe_leg
     return line
 
 

@@ -171,3 +171,28 @@ def test_mask_change_between_calls(x64):
         relax(g)
         ref(h)
         same(g, h)
+
+
+def test_element_indexing_on_device_level(x64):
+    """`u[i]` / `u[i] = v` on a device-resident level move one element and keep the level on
+    the device; slices still hand the level to the host."""
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def bump(u: f2) -> None:
+        u[0, 0] = u[0, 0] + 1.0
+
+    u = xgrid.Grid((6, 5), float)
+    u.now[...] = np.arange(30.0).reshape(6, 5)
+    bump(u)
+    assert u._ring[0].where == "device"
+    assert u[2, 3] == 14.0 and u[-1, -1] == 30.0 and u[(0, 0)] == 1.0
+    assert u._ring[0].where == "device"
+    u[2, 3] = -5.0
+    assert u._ring[0].where == "device"
+    bump(u)
+    assert u[2, 3] == -4.0                      # loads read the level the element write went to
+    assert u._data[1][2, 3] == -5.0
+    with pytest.raises(IndexError):
+        u[6, 0]
+    assert u[1].shape == (5,)                   # row slice -> NumPy view of the host mirror

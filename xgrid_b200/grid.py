@@ -132,11 +132,50 @@ class Grid:
     def now(self) -> np.ndarray:
         return self._host_view(0)
 
+    def _element_offset(self, key):
+        """Linear element offset for a full integer index (one element), else None."""
+        if isinstance(key, (int, np.integer)):
+            key = (key,)
+        if not (isinstance(key, tuple) and len(key) == self.dimension
+                and all(isinstance(k, (int, np.integer)) for k in key)):
+            return None
+        off = 0
+        for k, n in zip(key, self.shape):
+            k = int(k)
+            if k < 0:
+                k += n
+            if not 0 <= k < n:
+                raise IndexError(f"index {key} is out of bounds for grid of shape {self.shape}")
+            off = off * n + k
+        return off
+
     def __getitem__(self, key):
-        return self.now[key]
+        # element indexing on a device-resident level moves ONE element, not the level
+        # (the reference forwards to the NumPy array, xgrid/xgrid/__init__.py:82-86)
+        _flush()
+        lv = self._ring[0]
+        off = self._element_offset(key) if lv.where == "device" else None
+        if off is None:
+            return self.now[key]
+        out = np.empty(1, self.numpy_dtype)
+        rt = self._runtime()
+        rt.d2h(out.ctypes.data, lv.dev + off * self.itemsize, self.itemsize)
+        rt.sync()
+        return out[0]
 
     def __setitem__(self, key, value) -> None:
-        self.now[key] = value
+        _flush()
+        lv = self._ring[0]
+        off = self._element_offset(key) if lv.where == "device" else None
+        if off is None:
+            self.now[key] = value
+            return
+        src = np.empty(1, self.numpy_dtype)
+        src[0] = value
+        rt = self._runtime()
+        rt.h2d(lv.dev + off * self.itemsize, src.ctypes.data, self.itemsize)
+        rt.sync()
+        lv.halo_ok = False
 
     def fill(self, data: np.ndarray, time: int = 0) -> None:
         if data.shape != self.shape or data.dtype != self.numpy_dtype:
