@@ -28,11 +28,17 @@ import numpy as np
 from .log import Logger
 from .types import Boolean, Floating, Grid as GridT, Integer, Structure, Value, parse_annotation
 
+_schedule = None
+
+
 def _flush() -> None:
     """Execute deferred kernel calls (temporal-blocking queue) before grid state is observed."""
-    from .lang import schedule
-    if schedule._PENDING is not None:
-        schedule.flush_pending()
+    global _schedule
+    if _schedule is None:
+        from .lang import schedule
+        _schedule = schedule
+    if _schedule._PENDING is not None:
+        _schedule.flush_pending()
 
 
 SLACK = 64          # elements of linear slack before / after the padded array
@@ -318,7 +324,8 @@ class Grid:
 
     def _prepare_device(self, ghost_rows: int = 1) -> None:
         """Make every level and the mask resident before launches."""
-        self._ensure_ghost(ghost_rows)
+        if ghost_rows > self._ghost:
+            self._ensure_ghost(ghost_rows)
         for lv in self._ring:
             if lv.where != "device":
                 self._to_device(lv)

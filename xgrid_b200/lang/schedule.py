@@ -366,6 +366,20 @@ def flush_pending() -> None:
         p["program"]._run_batch(p["args"], p["grid"], p["count"])
 
 
+_Grid = None
+_Launcher = None
+_Runtime = None
+
+
+def _late_imports() -> None:
+    """grid / launch / shim import this module's siblings; resolve them once, not per call."""
+    global _Grid, _Launcher, _Runtime
+    from ..grid import Grid
+    from ..runtime.shim import Runtime
+    from .launch import Launcher
+    _Grid, _Launcher, _Runtime = Grid, Launcher, Runtime
+
+
 # --------------------------------------------------------------------------- Program
 class Program:
     """A compiled kernel: plan + generated module + launch logic."""
@@ -380,6 +394,8 @@ class Program:
         self.depth = self.ir.depth
         self.groups: list[cudagen.Group] = []
         self.plan = build_plan(self.ir.body, self.groups, None)
+        self._sig = self.ir.signature.arguments
+        self._typed_ok: dict = {}
         self.grid_args = [(n, t) for n, t in self.ir.signature.arguments if isinstance(t, GridT)]
         self.grid_ndims = {n: t.dimension for n, t in self.grid_args}
         Program._serial += 1
@@ -478,15 +494,19 @@ class Program:
         return self._call_now(args)
 
     def _bind(self, args):
-        from ..grid import Grid
-        sig = self.ir.signature.arguments
+        if _Grid is None:
+            _late_imports()
+        Grid = _Grid
+        sig = self._sig
         env, grids = {}, {}
         for (name, t), a in zip(sig, args):
             if isinstance(t, GridT):
                 if not isinstance(a, Grid):
                     raise TypeError(f"argument '{name}' must be an xgrid.Grid")
-                if a.dimension != t.dimension or a.element != t.element:
-                    raise TypeError(f"argument '{name}' expects {t!r}, got Grid({a.dimension}) of {a.element!r}")
+                if (id(a.typing), name) not in self._typed_ok:
+                    if a.dimension != t.dimension or a.element != t.element:
+                        raise TypeError(f"argument '{name}' expects {t!r}, got Grid({a.dimension}) of {a.element!r}")
+                    self._typed_ok[(id(a.typing), name)] = a.typing      # keeps the id alive
                 grids[name] = a
             elif isinstance(t, Pointer):
                 env[name] = a
@@ -499,7 +519,7 @@ class Program:
         return env, grids
 
     def _call_now(self, args):
-        sig = self.ir.signature.arguments
+        sig = self._sig
         env, grids = self._bind(args)
         # tick the field and resize the time ring (xgrid/lang/operator.py:37-39)
         for (name, t), a in zip(sig, args):
@@ -509,7 +529,7 @@ class Program:
         for g in grids.values():
             g._prepare_device(ghost)
 
-        from .launch import Launcher
+        Launcher = _Launcher
         sharded = any(g.sharded for g in grids.values())
         key = self._graph_key(env, grids) if (self.config.graphs and self.cacheable and self.groups
                                               and not sharded) else None
@@ -552,8 +572,9 @@ class Program:
         return result
 
     def _runtime(self):
-        from ..runtime.shim import Runtime
-        return Runtime.get()
+        if _Runtime is None:
+            _late_imports()
+        return _Runtime.get()
 
     def _run_batch(self, args, grid, count: int) -> None:
         """`count` deferred identical calls.  While at least T remain, one launch of the
