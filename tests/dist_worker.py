@@ -129,6 +129,23 @@ def main():
         ok = ok and np.array_equal(u1.now, h1.now[lo1:hi1]) and np.array_equal(u1._data[1], h1._data[1][lo1:hi1])
         from xgrid_b200.lang.launch import STATS
         ok = ok and STATS.get("multistep", 0) >= 2
+        # sharded cavity: implicit Jacobi sweeps + sparse Neumann statements that read level 0
+        # across the slab boundary (halo refresh between dependent groups)
+        nc = 96
+        mb, mp, mu, mv = W.cavity_masks(nc, nc)
+        dxc = 2.0 / (nc - 1)
+        cfg = W.Config(1.0, 0.1, 1e-4, dxc, dxc)
+        gs = [xgrid.Grid((nc, nc), float) for _ in range(4)]
+        hs = [HostGrid((nc, nc)) for _ in range(4)]
+        loc, hic = gs[0].row_range
+        for gg, hh, m in zip(gs, hs, (mb, mp, mu, mv)):
+            gg.boundary[...] = m[loc:hic]
+            hh.boundary[...] = m
+        for _ in range(2):
+            k["cavity_kernel"](*gs, cfg)
+            oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
+        for gg, hh in zip(gs, hs):
+            ok = ok and np.array_equal(gg.now, hh.now[loc:hic]) and np.array_equal(gg._data[1], hh._data[1][loc:hic])
         t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:

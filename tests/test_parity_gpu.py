@@ -458,3 +458,47 @@ def test_scalar_control_flow_around_sweeps(k64, tmp_path):
         stepper(u, 3 + calls, 0.1)
         ref(h, 3 + calls, 0.1)
     eq(u._data[0], h._data[0])
+
+
+def test_multistep_fp32_and_int(tmp_path):
+    """The deferred multi-step path for 4-byte element types (V = 4 lanes per 16-byte vector)."""
+    xgrid.init(cacheroot=str(tmp_path / "f32"))                  # precision="float"
+    k = W.make_kernels()
+    n = 40000
+    ic, dx = W.ic_1d(n, np.float32)
+    ic = (ic + 0.01 * np.random.default_rng(4).random(n)).astype(np.float32)
+    u, h = xgrid.Grid((n,), float), HostGrid((n,), np.float32)
+    u.now[...] = ic
+    h.now[...] = ic
+    u.boundary[0] = u.boundary[-1] = 1
+    h.boundary[0] = h.boundary[-1] = 1
+    from oracle.interp import Interp
+    ref = Interp(k["diffusion_1d"])
+    args = (0.01, 0.2 * dx * dx / 0.01, dx)
+    for _ in range(140):
+        k["diffusion_1d"](u, *args)
+        ref(h, *args)
+    eq(u._data[0], h._data[0], "fp32 L0")
+    eq(u._data[1], h._data[1], "fp32 L1")
+
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "i32"))
+    i1 = xgrid.grid[int, 1]
+
+    @xgrid.kernel()
+    def mix(a: i1, d: int) -> None:
+        a[0] = (a[-1] + a[1] + a[0] * 2) / d + a[0] % 5
+        with xgrid.boundary(1):
+            a[0] = 7
+
+    ici = np.random.default_rng(6).integers(-500, 500, n).astype(np.int32)
+    a, ha = xgrid.Grid((n,), int), HostGrid((n,), np.int32)
+    a.now[...] = ici
+    ha.now[...] = ici
+    a.boundary[0] = a.boundary[-1] = 1
+    ha.boundary[0] = ha.boundary[-1] = 1
+    refi = Interp(mix)
+    for _ in range(70):
+        mix(a, 4)
+        refi(ha, 4)
+    eq(a._data[0], ha._data[0], "int L0")
+    eq(a._data[1], ha._data[1], "int L1")

@@ -132,6 +132,9 @@ class Launcher:
             lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
             setattr(P, s.field, lv.dev)
         if lead.sharded:
+            if self.program.config.overstep != "none":
+                raise Exception("overstep='limit'/'wrap' is not supported on slab-sharded grids yet "
+                                "(the clamp / wrap would need the global extents)")
             self._refresh_halos(g)
         for m in g.masks:
             grid = self.grids[m]
