@@ -697,10 +697,14 @@ def _emit_march(g: Group, module: ModuleBuilder, V: int, R: int) -> str:
 
 
 # --------------------------------------------------------------------------- tiled (async pipeline) variant
-TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", str(56 * 1024)))
+TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", "0"))      # 0 = per-dimension default below
 TILED_TJ = int(_os.environ.get("XGB_TJ", "8"))
 TILED_WX3 = int(_os.environ.get("XGB_WX3", "1"))       # consumer warps side by side along k in 3-D
-TILED_NSV = int(_os.environ.get("XGB_NSV", "2"))
+TILED_NSV = int(_os.environ.get("XGB_NSV", "0"))         # 0 = per-dimension default below
+# measured on B200 (profiles/r1_experiments.md): 2-D likes 2 vectors per thread and ~56 KB rings
+# (4 CTAs/SM); 3-D amortises the per-plane bookkeeping better with 4 vectors per thread (256-column
+# tiles) and deeper rings (2 CTAs/SM)
+_TILED_DEFAULTS = {2: (2, 56 * 1024), 3: (4, 110 * 1024)}
 
 
 def tiled_config(g: Group):
@@ -713,7 +717,8 @@ def tiled_config(g: Group):
     if esize not in (4, 8):
         return None
     V = 16 // esize
-    NSV = TILED_NSV
+    NSV = TILED_NSV or _TILED_DEFAULTS[g.ndim][0]
+    budget = TILED_SMEM_BUDGET or _TILED_DEFAULTS[g.ndim][1]
     dmin = dmax = hj = hk = 0
     for a in g.stmts:
         for ld in a.sweep.loads:
@@ -734,7 +739,7 @@ def tiled_config(g: Group):
     if nread == 0:
         return None
     stage_bytes = nread * rp * wp * esize
-    ns = min(8, max((dmax - dmin) + 3, (TILED_SMEM_BUDGET - 256) // stage_bytes))
+    ns = min(8, max((dmax - dmin) + 3, (budget - 256) // stage_bytes))
     if 256 + ns * stage_bytes > 200 * 1024:
         return None
     return {"V": V, "NSV": NSV, "NCW": ncw, "TJ": tj, "WX": wx, "W": W, "HJ": hj, "HK": hk, "WP": wp,
@@ -802,9 +807,10 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     # ---------------- producer warp
     L.append("    if (warp == NCW) {")
     L.append("        const T *src[NREAD] = {" + ", ".join(f"p.{s.field}" for s in read_slots) + "};")
-    L.append("        for (int t = 0; t < planes; ++t) {")
-    L.append("            const int s = t % NS;")
-    L.append("            if (t >= NS) xgb::pipe::mbar_wait(&empty[s], ((t / NS) - 1) & 1);")
+    L.append("        int s = 0, eph = 1;                                // stage / parity of its previous release")
+    L.append("        for (int t = 0; t < planes; ++t, ++s) {")
+    L.append("            if (s == NS) { s = 0; eph ^= 1; }")
+    L.append("            if (t >= NS) xgb::pipe::mbar_wait(&empty[s], eph);")
     L.append("            if (lane == 0) xgb::pipe::mbar_expect_tx(&full[s], (uint32_t)(NREAD * RP * WP * sizeof(T)));")
     L.append("            __syncwarp();")
     L.append("            const int64_t plane = i0 + DMIN + t;")
@@ -836,15 +842,17 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
         L.append(f"    int fl_{m}[NSV];")
         L.append(f"#pragma unroll\n    for (int sv = 0; sv < NSV; ++sv) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv]);")
     L.append("    const T *srow = stages + (int64_t)(ty + HJ) * WP + HK;   // this warp's row inside a plane")
-    L.append("    int tn = 0;                                           // newest plane waited for")
-    L.append("    for (; tn < DSPAN; ++tn) xgb::pipe::mbar_wait(&full[tn % NS], (tn / NS) & 1);")
+    L.append("    int fs = 0, fph = 0;                                  // stage / parity of the newest plane")
+    L.append("    for (int t = 0; t < DSPAN; ++t) { xgb::pipe::mbar_wait(&full[fs], fph); if (++fs == NS) { fs = 0; fph ^= 1; } }")
     L.append("    int ps = 0;                                           // stage of plane o + DMIN")
-    L.append("    for (int64_t o = i0; o < iend; ++o, ++tn) {")
+    L.append("    const int nout = (int)(iend - i0);")
+    L.append("    for (int it = 0; it < nout; ++it) {")
     for m in g.masks:
         L.append(f"        int fc_{m}[NSV];")
         L.append(f"#pragma unroll\n        for (int sv = 0; sv < NSV; ++sv) {{ fc_{m}[sv] = fl_{m}[sv]; "
-                 f"if (o + 1 < iend) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv] + S0); }}")
-    L.append("        xgb::pipe::mbar_wait(&full[tn % NS], (tn / NS) & 1);")
+                 f"if (it + 1 < nout) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv] + S0); }}")
+    L.append("        xgb::pipe::mbar_wait(&full[fs], fph);")
+    L.append("        if (++fs == NS) { fs = 0; fph ^= 1; }")
     # stage base of every input plane this output plane reads (once per plane, not per tap)
     dis = sorted({key[1] for key in windows})
     for di in dis:
