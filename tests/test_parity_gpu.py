@@ -502,3 +502,86 @@ def test_multistep_fp32_and_int(tmp_path):
         refi(ha, 4)
     eq(a._data[0], ha._data[0], "int L0")
     eq(a._data[1], ha._data[1], "int L1")
+
+
+# --------------------------------------------------------------------------- 2-D two-steps-per-pass (tiled2)
+def _tiled2_kernels():
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def wide(u: f2, a: float) -> None:
+        c = a * 0.5
+        u[0, 0] = 0.1 * u[2, 0] + 0.1 * u[-2, 1] + 0.2 * u[0, -2] + 0.3 * u[1, 2] + c * u[0, 0] - 0.05 * u[-1, -1]
+        with xgrid.boundary(1):
+            u[0, 0] = 0.75
+        with xgrid.boundary(2):
+            u[0, 0] = 0.5 * (u[0, 1] + u[1, 0]) - a
+
+    @xgrid.kernel()
+    def upwind(u: f2, cx: float, cy: float) -> None:
+        u[0, 0] = u[0, 0] - cx * (u[0, 0] - u[-1, 0]) - cy * (u[0, 0] - u[0, -1])
+        with xgrid.boundary(1):
+            u[0, 0] = 1.0
+
+    return wide, upwind
+
+
+@pytest.mark.parametrize("which,shape,calls", [
+    ("wide", (300, 2050), 7), ("wide", (64, 1024), 4), ("upwind", (130, 3000), 9), ("wide", (257, 1030), 2),
+])
+def test_tiled2_matches_step_at_a_time(tmp_path, which, shape, calls):
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    from oracle.interp import Interp
+    from xgrid_b200.lang.launch import STATS
+    wide, upwind = _tiled2_kernels()
+    kern, args = (wide, (0.3,)) if which == "wide" else (upwind, (0.2, 0.15))
+    rng = np.random.default_rng(shape[0])
+    ic = rng.random(shape)
+    mask = np.zeros(shape, np.int32)
+    mask[0, :] = mask[-1, :] = 1
+    mask[:, 0] = mask[:, -1] = 1
+    if which == "wide":
+        sp = rng.random(shape)
+        mask[sp < 0.01] = 2
+        mask[sp > 0.995] = 1
+    u, h = make_grid(ic, mask), HostGrid(shape)
+    h.now[...] = ic
+    h.boundary[...] = mask
+    ref = Interp(kern)
+    before = STATS.get("tiled2", 0)
+    for _ in range(calls):
+        kern(u, *args)
+        ref(h, *args)
+    eq(u._data[0], h._data[0], "L0")
+    eq(u._data[1], h._data[1], "L1")
+    assert STATS.get("tiled2", 0) == before + calls // 2
+    u.now[5:9, 100:200] = 2.5           # host write, then continue
+    h.now[5:9, 100:200] = 2.5
+    for _ in range(5):
+        kern(u, *args)
+        ref(h, *args)
+    eq(u._data[0], h._data[0], "L0 after host write")
+    eq(u._data[1], h._data[1], "L1 after host write")
+
+
+def test_tiled2_falls_back_when_a_mask_value_has_no_statement(tmp_path):
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    from oracle.interp import Interp
+    from xgrid_b200.lang.launch import STATS
+    wide, _ = _tiled2_kernels()
+    shape = (128, 1024)
+    ic = np.random.default_rng(1).random(shape)
+    mask = np.zeros(shape, np.int32)
+    mask[0, :] = 1
+    mask[40, 500] = 7                   # never written: needs the level two steps back (F5)
+    u, h = make_grid(ic, mask), HostGrid(shape)
+    h.now[...] = ic
+    h.boundary[...] = mask
+    ref = Interp(wide)
+    before = STATS.get("tiled2", 0)
+    for _ in range(6):
+        wide(u, 0.3)
+        ref(h, 0.3)
+    eq(u._data[0], h._data[0])
+    eq(u._data[1], h._data[1])
+    assert STATS.get("tiled2", 0) == before

@@ -27,6 +27,7 @@ VARIANT_SPARSE = "sparse"
 VARIANT_MARCH = "march"
 VARIANT_TILED = "tiled"
 VARIANT_MULTISTEP = "multistep"
+VARIANT_TILED2 = "tiled2"
 MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
 import os as _os
 # rows loaded ahead of use per chain; 0 = off (measured: register prefetch costs occupancy, the
@@ -72,6 +73,7 @@ class Group:
     march: bool = False                           # has axis-0 marching variants
     tiled: dict | None = None                     # geometry of the async shared-memory pipeline variant
     multistep: dict | None = None                 # temporal-blocking variant (1-D, whole-kernel groups)
+    tiled2: dict | None = None                    # two time steps per pass, 2-D (time-skewed tiled pipeline)
 
     def slot(self, grid: str, level) -> Slot:
         for s in self.slots:
@@ -349,6 +351,7 @@ def build_params(g: Group, module: ModuleBuilder, scope_types: dict, grid_ndims:
     add("const int64_t* __restrict__", "list", ctypes.c_void_p)
     add("int64_t", "count", ctypes.c_int64)
     add("int64_t", "chunk0", ctypes.c_int64)     # axis-0 points per CTA in the marching variant
+    add("int64_t", "opt0", ctypes.c_int64)       # variant-specific flag (tiled2: also write the middle level)
     add("int64_t", "open_lo", ctypes.c_int64)    # slab has a neighbour below / above: its ghost points
     add("int64_t", "open_hi", ctypes.c_int64)    # are real grid points (multi-step variant)
     add("int64_t", "r_lo", ctypes.c_int64)       # axis-0 range [r_lo, r_hi) swept by this launch
@@ -409,6 +412,9 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
             g.multistep = multistep_config(g)
             if g.multistep is not None:
                 module.kernels.append(_emit_multistep(g, module, g.multistep))
+            g.tiled2 = tiled2_config(g)
+            if g.tiled2 is not None:
+                module.kernels.append(_emit_tiled2(g, module, g.tiled2))
         else:
             module.kernels.append(_emit_general(g, module, VARIANT_DENSE))
             module.kernels.append(_emit_general(g, module, VARIANT_SPARSE))
@@ -1087,5 +1093,208 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("        }")
     L.append("    }")
     L.append("    #undef XSW")
+    L.append("}")
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------- tiled2: two time steps per pass (2-D)
+def tiled2_config(g: Group):
+    """2-D groups that read only the previous level of the ONE grid they update can advance two
+    time steps per pass: rows stream through the bulk-copy pipeline once, the first step's rows
+    live in a small shared-memory ring, the second step is written to HBM."""
+    if g.ndim != 2 or g.implicit or g.sparse or g.tiled is None:
+        return None
+    if {s.grid for s in g.slots} != {g.slots[0].grid}:
+        return None
+    if {(s.level, s.read, s.written) for s in g.slots} != {(0, False, True), (1, True, False)}:
+        return None
+    elem = g.slots[0].elem
+    if isinstance(elem, (Structure, Boolean)) or elem.width_bytes != 8:
+        return None
+    V, NSV, NCW = 2, 2, 8
+    dmin = dmax = hk = 0
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            dmin, dmax = min(dmin, ld.space_offset[0]), max(dmax, ld.space_offset[0])
+            hk = max(hk, abs(ld.space_offset[-1]))
+    if dmax - dmin > 4 or hk > 4:
+        return None
+    W = NCW * 32 * V * NSV
+    hkm = -(-hk // V) * V                 # halo of the middle rows
+    hk0 = -(-2 * hk // V) * V             # halo of the input rows
+    wp0, wpm = W + 2 * hk0, W + 2 * hkm
+    dspan = dmax - dmin
+    mr = dspan + 2                        # middle-row ring
+    ns = max(dspan + 2, int(_os.environ.get("XGB_T2_NS", "5")))      # input-row ring (3 CTAs/SM at 5)
+    smem = 256 + ns * wp0 * 8 + mr * wpm * 8
+    return {"V": V, "NSV": NSV, "NCW": NCW, "W": W, "HK": hk, "HKM": hkm, "HK0": hk0, "WP0": wp0, "WPM": wpm,
+            "DMIN": dmin, "DMAX": dmax, "MR": mr, "NS": ns, "smem": smem, "threads": (NCW + 1) * 32,
+            "ghost": 2 * max(abs(dmin), abs(dmax), 1)}
+
+
+def _emit_tiled2(g: Group, module: ModuleBuilder, c: dict) -> str:
+    """Time-skewed two-step sweep.  For output row o (step 2) the middle rows o+DMIN..o+DMAX
+    (step 1) are needed, each of which needs input rows q+DMIN..q+DMAX.  Input rows stream in
+    order; when row r lands the consumers compute middle row q = r - DMAX into the middle ring,
+    meet at a named barrier, and then compute output row o = q - DMAX from the middle ring.
+    Every shared-memory position is identified with its LINEAR grid index, so columns outside a
+    row read / produce exactly what the step-at-a-time sweeps do (linear addressing, F10);
+    positions outside the array are ghost zeros.  The launcher guarantees that every mask value
+    present in the grid has a statement, so every cell is rewritten each step and the level two
+    steps back is never needed."""
+    T = module.ctype(g.slots[0].elem)
+    gname = g.slots[0].grid
+    V = c["V"]
+    hoist: dict = {}
+    # row windows per axis-0 offset: [lo, hi] over the contiguous-axis offsets
+    win: dict = {}
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            lo, hi = win.get(ld.space_offset[0], (0, 0))
+            win[ld.space_offset[0]] = (min(lo, ld.space_offset[-1]), max(hi, ld.space_offset[-1]))
+
+    def tap(e: ir.Stencil) -> str:
+        lo, _ = win[e.space_offset[0]]
+        return f"w{e.space_offset[0] - c['DMIN']}[v + {e.space_offset[-1] - lo}]"
+
+    emit = ExprEmitter(module, _ident, tap, hoist)
+    slow = [f"if (m[v] == {a.sweep.mask}) val[v] = {emit(a.value)};" for a in g.stmts]
+    fast = [f"val[v] = {emit(a.value)};" for a in g.stmts if a.sweep.mask == 0][-1:]
+
+    def windows(prefix: str, ind: str) -> list:
+        return [f"{ind}T w{d0 - c['DMIN']}[V + {hi - lo}]; xgb::lds_window<T, V, {lo}, {hi}>({prefix}{d0 - c['DMIN']} + kk, w{d0 - c['DMIN']});"
+                for d0, (lo, hi) in win.items()]
+
+    def body(prefix: str, ind: str) -> list:
+        out = [f"{ind}T val[V];", f"{ind}if (fl == 0) {{"]
+        out += windows(prefix, ind + "    ")
+        out += ["#pragma unroll", f"{ind}    for (int v = 0; v < V; ++v) {{ " + " ".join(fast) + " }", f"{ind}}} else {{"]
+        out += [f"{ind}    int m[V]; xgb::ld_mask_flagged<V>(p.m_{gname}, fl, lin, m);"]
+        out += windows(prefix, ind + "    ")
+        out += ["#pragma unroll", f"{ind}    for (int v = 0; v < V; ++v) {{ val[v] = T(0); " + " ".join(slow) + " }", f"{ind}}}"]
+        return out
+
+    name = kernel_name(g, VARIANT_TILED2, V)
+    nit1 = -(-c["WPM"] // (c["NCW"] * 32 * V))
+    nit2 = c["W"] // (c["NCW"] * 32 * V)
+    L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int V = {V}, NCW = {c['NCW']}, NT = NCW * 32, W = {c['W']}, HKM = {c['HKM']}, HK0 = {c['HK0']}, WP0 = {c['WP0']}, "
+             f"WPM = {c['WPM']}, NS = {c['NS']}, MR = {c['MR']}, DMIN = {c['DMIN']}, DMAX = {c['DMAX']}, DSPAN = DMAX - DMIN, "
+             f"NIT1 = {nit1}, NIT2 = {nit2};")
+    L.append(f"    typedef {T} T;")
+    L.append("    extern __shared__ __align__(128) unsigned char xgb_smem[];")
+    L.append("    uint64_t *full = reinterpret_cast<uint64_t *>(xgb_smem);")
+    L.append("    uint64_t *empty = full + NS;")
+    L.append("    T *stages = reinterpret_cast<T *>(xgb_smem + 256);        // [NS][WP0]   input rows (u^n)")
+    L.append("    T *mids = stages + NS * WP0;                              // [MR][WPM]   middle rows (u^{n+1})")
+    L.append("    const T *src = static_cast<const T *>(p.aux0);")
+    L.append("    T *out2 = static_cast<T *>(p.aux1), *out1 = static_cast<T *>(p.aux2);")
+    L.append("    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+    L.append("    const int64_t c0 = (int64_t)blockIdx.x * W;")
+    L.append("    const int64_t i0 = p.r_lo + ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * p.chunk0;")
+    L.append("    if (i0 >= p.r_hi) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.r_hi) ? (i0 + p.chunk0) : p.r_hi;")
+    L.append("    const int64_t S0 = p.cols, total = p.n0 * p.cols;")
+    L.append("    const int nrows = (int)(iend - i0) + 2 * DSPAN;              // input rows this CTA streams")
+    L.append("    if (threadIdx.x == 0) {")
+    L.append("        for (int s = 0; s < NS; ++s) { xgb::pipe::mbar_init(&full[s], 1); xgb::pipe::mbar_init(&empty[s], NCW); }")
+    L.append("        xgb::pipe::fence_barrier_init();")
+    L.append("    }")
+    L.append("    __syncthreads();")
+    L.append("    if (warp == NCW) {                                         // producer: one bulk copy per input row")
+    L.append("        int s = 0, eph = 1;")
+    L.append("        const T *row = src + ((i0 + 2 * DMIN) * S0 + (c0 - HK0));")
+    L.append("        for (int t = 0; t < nrows; ++t, ++s, row += S0) {")
+    L.append("            if (s == NS) { s = 0; eph ^= 1; }")
+    L.append("            if (t >= NS) xgb::pipe::mbar_wait(&empty[s], eph);")
+    L.append("            if (lane == 0) {")
+    L.append("                xgb::pipe::mbar_expect_tx(&full[s], (uint32_t)(WP0 * sizeof(T)));")
+    L.append("                xgb::pipe::bulk_g2s(stages + s * WP0, row, (uint32_t)(WP0 * sizeof(T)), &full[s]);")
+    L.append("            }")
+    L.append("            __syncwarp();")
+    L.append("        }")
+    L.append("        return;")
+    L.append("    }")
+    L.extend(hoist_lines(hoist))
+    L.append("    const int tid = warp * 32 + lane;                           // consumer thread 0..255")
+    L.append("    int fs = 0, fph = 0, rs = 0, ms = 0;                        // newest input stage / parity; oldest live stage; middle slot")
+    L.append("    int64_t lin_mid = (i0 + DMIN) * S0 + (c0 - HKM);            // linear index of the next middle row's first column")
+    L.append("    int64_t lin_out = i0 * S0 + c0;")
+    L.append("    for (int t = 0; t < nrows; ++t) {")
+    L.append("        xgb::pipe::mbar_wait(&full[fs], fph);")
+    L.append("        if (t >= DSPAN) {")
+    L.append("            // ---- step 1: middle row q = i0 + DMIN + (t - DSPAN) over columns [c0 - HKM, c0 + W + HKM)")
+    for d0 in win:
+        k = c["DMAX"] - d0
+        L.append(f"            const T *in{d0 - c['DMIN']} = stages + ((fs >= {k}) ? (fs - {k}) : (fs - {k} + NS)) * WP0 + (HK0 - HKM);")
+    L.append("            T *mrow = mids + ms * WPM;")
+    L.append("            const bool row_in = (lin_mid >= 0) && (lin_mid + WPM <= total);")
+    L.append("            int fls[NIT1];")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT1; ++i) {                       // flag bytes first: their latency overlaps")
+    L.append("                const int kk = (tid + i * NT) * V;")
+    L.append("                const int64_t lin = lin_mid + kk;")
+    L.append("                fls[i] = -1;")
+    L.append(f"                if (kk < WPM && (row_in || (lin >= 0 && lin + V <= total))) fls[i] = xgb::ld_flag(p.m_{gname}, p.f_{gname}, lin);")
+    L.append("            }")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT1; ++i) {")
+    L.append("                const int kk = (tid + i * NT) * V;")
+    L.append("                if (kk < WPM) {")
+    L.append("                    const int fl = fls[i];")
+    L.append("                    const int64_t lin = lin_mid + kk;")
+    L.append("                    if (fl >= 0) {")
+    L.extend(body("in", "                        "))
+    L.append("                        xgb::st_vec<T, V>(mrow + kk, val);")
+    L.append("                    } else {")
+    L.append("                        T z[V];")
+    L.append("#pragma unroll")
+    L.append("                        for (int v = 0; v < V; ++v) z[v] = T(0);         // outside the array: ghost zeros")
+    L.append("                        xgb::st_vec<T, V>(mrow + kk, z);")
+    L.append("                    }")
+    L.append("                }")
+    L.append("            }")
+    L.append("            lin_mid += S0;")
+    L.append("            asm volatile(\"bar.sync 1, %0;\" :: \"n\"(NT) : \"memory\");      // middle row complete")
+    L.append("        }")
+    L.append("        if (t >= 2 * DSPAN) {")
+    L.append("            // ---- step 2: output row o = i0 + (t - 2*DSPAN) over the CTA's own columns; middle row o+d0 sits")
+    L.append("            //      (DMAX - d0) slots behind the one just written")
+    for d0 in win:
+        k = c["DMAX"] - d0
+        L.append(f"            const T *md{d0 - c['DMIN']} = mids + ((ms >= {k}) ? (ms - {k}) : (ms - {k} + MR)) * WPM + HKM;")
+    if 0 not in win:
+        k = c["DMAX"]
+        L.append(f"            const T *md{0 - c['DMIN']} = mids + ((ms >= {k}) ? (ms - {k}) : (ms - {k} + MR)) * WPM + HKM;")
+    L.append("            int fls[NIT2];")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT2; ++i) {")
+    L.append("                const int kk = (tid + i * NT) * V;")
+    L.append("                fls[i] = -1;")
+    L.append(f"                if (c0 + kk < p.cols) fls[i] = xgb::ld_flag(p.m_{gname}, p.f_{gname}, lin_out + kk);")
+    L.append("            }")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT2; ++i) {")
+    L.append("                const int kk = (tid + i * NT) * V;")
+    L.append("                const int fl = fls[i];")
+    L.append("                if (fl >= 0) {")
+    L.append("                    const int64_t lin = lin_out + kk;")
+    L.extend(body("md", "                    "))
+    L.append("                    xgb::st_vec<T, V>(out2 + lin, val);")
+    L.append("                    if (p.opt0) {                                     // last pass of a batch: u^{n+1} is observable")
+    L.append(f"                        T mv[V]; xgb::ld_vec<T, V>(md{0 - c['DMIN']} + kk, mv); xgb::st_vec<T, V>(out1 + lin, mv);")
+    L.append("                    }")
+    L.append("                }")
+    L.append("            }")
+    L.append("            lin_out += S0;")
+    L.append("        }")
+    L.append("        if (t >= DSPAN) {                                           // input row q + DMIN is dead")
+    L.append("            __syncwarp();")
+    L.append("            if (lane == 0) xgb::pipe::mbar_arrive(&empty[rs]);")
+    L.append("            rs = (rs + 1 == NS) ? 0 : rs + 1;")
+    L.append("            ms = (ms + 1 == MR) ? 0 : ms + 1;")
+    L.append("        }")
+    L.append("        if (++fs == NS) { fs = 0; fph ^= 1; }")
+    L.append("    }")
     L.append("}")
     return "\n".join(L) + "\n"

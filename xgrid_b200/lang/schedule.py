@@ -356,6 +356,7 @@ class _Interpreter:
 _PENDING = None          # {"program", "args", "grid", "key", "count"}: identical calls not yet executed
 PENDING_LIMIT = 4096
 MULTISTEP_MIN_POINTS = int(os.environ.get("XGB_MS_MIN", "16384"))
+TILED2_ENABLED = os.environ.get("XGB_TILED2", "1") != "0"
 
 
 def flush_pending() -> None:
@@ -422,6 +423,18 @@ class Program:
             self.batchable = True
             self._grid_pos = [n for n, (_, t) in enumerate(self.ir.signature.arguments)
                               if isinstance(t, GridT)][0]
+        # two-steps-per-pass variant for 2-D kernels (same program shape, one 2-D group)
+        self.batchable2 = False
+        if (len(self.groups) == 1 and self.groups[0].tiled2 is not None and self.depth == 2
+                and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
+                and isinstance(self.ir.signature.return_type, Void)
+                and isinstance(self.plan[-1], GroupNode)
+                and all(isinstance(n, tuple) and n[0] == "stmt" and isinstance(n[1], ir.Assignment)
+                        for n in self.plan[:-1])
+                and not any(isinstance(t, (Pointer, Structure)) for _, t in self.ir.signature.arguments)):
+            self.batchable2 = True
+            self._grid_pos = [n for n, (_, t) in enumerate(self.ir.signature.arguments)
+                              if isinstance(t, GridT)][0]
         self._graphs: dict = {}
         self._seen: set = set()
         self._image = None
@@ -475,10 +488,16 @@ class Program:
         if len(args) != len(sig):
             # xgrid/util/ffi.py:31-33
             raise TypeError(f"this function takes {len(sig)} argument ({len(args)} given)")
-        if self.batchable and self.config.temporal:
-            # defer: a run of identical calls is executed T steps per launch on flush
+        if (self.batchable or self.batchable2) and self.config.temporal:
+            # defer: a run of identical calls is executed several steps per launch on flush
             grid = args[self._grid_pos]
-            if getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and grid.dimension == 1:
+            if self.batchable:
+                defer = getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and grid.dimension == 1
+            else:
+                t2 = self.groups[0].tiled2
+                defer = (getattr(grid, "dimension", 0) == 2 and not grid.sharded and TILED2_ENABLED
+                         and grid.shape[1] >= t2["W"] and grid.shape[1] % t2["V"] == 0 and grid.shape[0] >= 64)
+            if defer:
                 key = tuple(a for n, a in enumerate(args) if n != self._grid_pos)
                 p = _PENDING
                 if p is not None and p["program"] is self and p["grid"] is grid and p["key"] == key \
@@ -576,11 +595,77 @@ class Program:
             _late_imports()
         return _Runtime.get()
 
+    def _run_batch2(self, args, grid, count: int) -> None:
+        """2-D: `count` deferred identical calls, two time steps per pass (cudagen._emit_tiled2).
+        A pass reads level 0 and writes u^{n+2} into the buffer of the dead level 1; only the last
+        pass of the batch also stores the middle level u^{n+1} (into a spare buffer), because the
+        intermediate ones are overwritten before anything can observe them."""
+        g = self.groups[0]
+        cfg = g.tiled2
+        passes = count // 2
+        done = 0
+        if passes:
+            env, grids = self._bind(args)
+            captured = []
+            _Interpreter(self.ir, env, grids, lambda grp, e: captured.append(dict(e))).run(self.plan)
+            env = captured[0]
+            rt = self._runtime()
+            grid._extend_time(2)
+            grid._prepare_device(cfg["ghost"])
+            # every cell must be rewritten each step: all mask values present need a statement
+            handled = {a.sweep.mask for a in g.stmts}
+            present = {k for k in range(255) if grid._mask_count(k) > 0}
+            if not present <= handled:
+                passes = 0
+        if passes:
+            fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_TILED2, cfg["V"]), cfg["smem"])
+            P = g.params_cls()
+            n0, cols = grid.shape
+            P.n0, P.n1, P.rows, P.cols = n0, cols, n0, cols
+            P.r_lo, P.r_hi = 0, n0
+            gname = g.slots[0].grid
+            setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
+            setattr(P, f"f_{gname}", grid._flags_dev if grid._mask_any else None)
+            from .launch import Launcher, STATS, TUNE
+            marshal = Launcher(self, grids)
+            for name, t in g.scalars.items():
+                setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
+            gx = (cols + cfg["W"] - 1) // cfg["W"]
+            want = max(1, -(-TUNE["min_ctas"] // gx))
+            chunk0 = max(64, -(-n0 // want))
+            chunks = (n0 + chunk0 - 1) // chunk0
+            gy = min(chunks, 65535)
+            P.chunk0 = chunk0
+            geometry = ((gx, gy, (chunks + gy - 1) // gy), (cfg["threads"], 1, 1))
+            for pi in range(passes):
+                x0, x1 = grid._ring[0], grid._ring[1]
+                last = pi == passes - 1
+                P.aux0, P.aux1 = x0.dev, x1.dev
+                if last:
+                    d = grid._spare_levels(1)[0]
+                    P.aux2, P.opt0 = d.dev, 1
+                else:
+                    P.aux2, P.opt0 = None, 0
+                rt.launch(fn, geometry[0], geometry[1], P, smem=cfg["smem"])
+                STATS["tiled2"] = STATS.get("tiled2", 0) + 1
+                if last:
+                    grid._ring, grid._spares = [x1, d], [x0] + grid._spares[1:]
+                else:
+                    grid._ring = [x1, x0]
+                for lv in grid._ring:
+                    lv.where = "device"
+                    lv.halo_ok = False
+                done += 2
+        for _ in range(count - done):
+            self._call_now(args)
+
     def _run_batch(self, args, grid, count: int) -> None:
         """`count` deferred identical calls.  While at least T remain, one launch of the
         multi-step kernel advances T time steps: it reads the two ring levels, iterates in
         shared memory and writes the two newest levels into spare buffers that then become
         the ring (T is even, so the ring order equals the order after T single ticks)."""
+        if grid.dimension == 2:
+            return self._run_batch2(args, grid, count)
         g = self.groups[0]
         cfg = g.multistep
         T = cfg["T"]
