@@ -585,3 +585,41 @@ def test_tiled2_falls_back_when_a_mask_value_has_no_statement(tmp_path):
     eq(u._data[0], h._data[0])
     eq(u._data[1], h._data[1])
     assert STATS.get("tiled2", 0) == before
+
+
+@pytest.mark.parametrize("shape,calls", [((70, 24, 256), 5), ((64, 13, 300), 4), ((96, 8, 128), 3)])
+def test_tiled2_3d_matches_step_at_a_time(tmp_path, monkeypatch, shape, calls):
+    """The 3-D two-steps-per-pass variant is opt-in (slower than the single-step kernel on B200);
+    it must still be exact."""
+    from xgrid_b200.lang import cudagen
+    monkeypatch.setattr(cudagen, "TILED2_3D", True)
+    xgrid.init(precision="double", cacheroot=str(tmp_path))
+    from oracle.interp import Interp
+    from xgrid_b200.lang.launch import STATS
+    f3 = xgrid.grid[float, 3]
+
+    @xgrid.kernel()
+    def skew(u: f3, a: float) -> None:
+        u[0, 0, 0] = u[0, 0, 0] + a * (u[1, 0, 0] + u[-1, 1, 0] + u[0, 1, -1] + u[0, -1, 0] + u[0, 0, 1] + u[1, 0, -1]
+                                       - 6.0 * u[0, 0, 0])
+        with xgrid.boundary(1):
+            u[0, 0, 0] = 0.25
+        with xgrid.boundary(2):
+            u[0, 0, 0] = u[0, 0, 0] * 0.5 + u[0, 1, 0] * 0.25
+
+    rng = np.random.default_rng(shape[1])
+    ic = rng.random(shape)
+    mask = W.shell_mask(shape)
+    sp = rng.random(shape)
+    mask[sp < 0.01] = 2
+    u, h = make_grid(ic, mask), HostGrid(shape)
+    h.now[...] = ic
+    h.boundary[...] = mask
+    ref = Interp(skew)
+    before = STATS.get("tiled2", 0)
+    for _ in range(calls):
+        skew(u, 0.1)
+        ref(h, 0.1)
+    eq(u._data[0], h._data[0], "L0")
+    eq(u._data[1], h._data[1], "L1")
+    assert STATS.get("tiled2", 0) == before + calls // 2

@@ -414,7 +414,7 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
                 module.kernels.append(_emit_multistep(g, module, g.multistep))
             g.tiled2 = tiled2_config(g)
             if g.tiled2 is not None:
-                module.kernels.append(_emit_tiled2(g, module, g.tiled2))
+                module.kernels.append((_emit_tiled2_3d if g.ndim == 3 else _emit_tiled2)(g, module, g.tiled2))
         else:
             module.kernels.append(_emit_general(g, module, VARIANT_DENSE))
             module.kernels.append(_emit_general(g, module, VARIANT_SPARSE))
@@ -1102,6 +1102,8 @@ def tiled2_config(g: Group):
     """2-D groups that read only the previous level of the ONE grid they update can advance two
     time steps per pass: rows stream through the bulk-copy pipeline once, the first step's rows
     live in a small shared-memory ring, the second step is written to HBM."""
+    if g.ndim == 3:
+        return tiled2_config_3d(g)
     if g.ndim != 2 or g.implicit or g.sparse or g.tiled is None:
         return None
     if {s.grid for s in g.slots} != {g.slots[0].grid}:
@@ -1289,6 +1291,214 @@ def _emit_tiled2(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("            lin_out += S0;")
     L.append("        }")
     L.append("        if (t >= DSPAN) {                                           // input row q + DMIN is dead")
+    L.append("            __syncwarp();")
+    L.append("            if (lane == 0) xgb::pipe::mbar_arrive(&empty[rs]);")
+    L.append("            rs = (rs + 1 == NS) ? 0 : rs + 1;")
+    L.append("            ms = (ms + 1 == MR) ? 0 : ms + 1;")
+    L.append("        }")
+    L.append("        if (++fs == NS) { fs = 0; fph ^= 1; }")
+    L.append("    }")
+    L.append("}")
+    return "\n".join(L) + "\n"
+
+
+# --------------------------------------------------------------------------- tiled2 in 3-D
+# opt-in: measured slower than the single-step tiled kernel on heat3d (instruction-bound, 0.67 vs
+# 0.83 of the HBM roofline; profiles/r1_experiments.md)
+TILED2_3D = _os.environ.get("XGB_TILED2_3D", "0") != "0"
+
+
+def tiled2_config_3d(g: Group):
+    """Same two-steps-per-pass scheme with (j, k) planes: a CTA owns a TJ x W tile, the middle
+    planes cover the tile plus one stencil halo, the input planes plus two."""
+    if not TILED2_3D or g.implicit or g.sparse or g.tiled is None:
+        return None
+    if {s.grid for s in g.slots} != {g.slots[0].grid}:
+        return None
+    if {(s.level, s.read, s.written) for s in g.slots} != {(0, False, True), (1, True, False)}:
+        return None
+    elem = g.slots[0].elem
+    if isinstance(elem, (Structure, Boolean)) or elem.width_bytes != 8:
+        return None
+    V, NCW = 2, 8
+    dmin = dmax = hj = hk = 0
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            off = ld.space_offset
+            dmin, dmax = min(dmin, off[0]), max(dmax, off[0])
+            hj, hk = max(hj, abs(off[1])), max(hk, abs(off[2]))
+    if dmax - dmin > 2 or hj > 2 or hk > 2:
+        return None
+    TJ, W = int(_os.environ.get("XGB_T2_TJ", "8")), int(_os.environ.get("XGB_T2_W", "128"))
+    hkm = -(-hk // V) * V
+    hk0 = -(-(hkm + hk) // V) * V
+    wpm, wp0 = W + 2 * hkm, W + 2 * hk0
+    rpm, rp0 = TJ + 2 * hj, TJ + 4 * hj
+    dspan = dmax - dmin
+    mr = dspan + 2
+    ns = max(dspan + 2, int(_os.environ.get("XGB_T2_NS3", "5")))
+    smem = 256 + ns * rp0 * wp0 * 8 + mr * rpm * wpm * 8
+    if smem > 200 * 1024:
+        return None
+    return {"V": V, "NCW": NCW, "TJ": TJ, "W": W, "HJ": hj, "HK": hk, "HKM": hkm, "HK0": hk0, "WPM": wpm, "WP0": wp0,
+            "RPM": rpm, "RP0": rp0, "DMIN": dmin, "DMAX": dmax, "MR": mr, "NS": ns, "smem": smem,
+            "threads": (NCW + 1) * 32, "ghost": 2 * max(abs(dmin), abs(dmax), 1)}
+
+
+def _emit_tiled2_3d(g: Group, module: ModuleBuilder, c: dict) -> str:
+    """3-D twin of _emit_tiled2: stages and middle slots hold (j, k) planes; the consumers walk
+    the plane regions as flattened vector lists.  Shared-memory positions keep their linear grid
+    index (plane * S0 + j * n2 + k with j, k possibly outside their ranges), so wrap reads behave
+    exactly as in the step-at-a-time sweeps."""
+    T = module.ctype(g.slots[0].elem)
+    gname = g.slots[0].grid
+    V = c["V"]
+    hoist: dict = {}
+    win: dict = {}          # (d0, dj) -> [lo, hi] over dk
+    for a in g.stmts:
+        for ld in a.sweep.loads:
+            key = (ld.space_offset[0], ld.space_offset[1])
+            lo, hi = win.get(key, (0, 0))
+            win[key] = (min(lo, ld.space_offset[2]), max(hi, ld.space_offset[2]))
+    wname = {key: f"w{n}" for n, key in enumerate(win)}
+
+    def tap(e: ir.Stencil) -> str:
+        key = (e.space_offset[0], e.space_offset[1])
+        return f"{wname[key]}[v + {e.space_offset[2] - win[key][0]}]"
+
+    emit = ExprEmitter(module, _ident, tap, hoist)
+    slow = [f"if (m[v] == {a.sweep.mask}) val[v] = {emit(a.value)};" for a in g.stmts]
+    fast = [f"val[v] = {emit(a.value)};" for a in g.stmts if a.sweep.mask == 0][-1:]
+
+    def windows(prefix: str, pitch: str, ind: str) -> list:
+        return [f"{ind}T {wname[k]}[V + {hi - lo}]; xgb::lds_window<T, V, {lo}, {hi}>({prefix}{k[0] - c['DMIN']} + (jj + ({k[1]})) * {pitch} + kk, {wname[k]});"
+                for k, (lo, hi) in win.items()]
+
+    def body(prefix: str, pitch: str, ind: str) -> list:
+        out = [f"{ind}T val[V];", f"{ind}if (fl == 0) {{"]
+        out += windows(prefix, pitch, ind + "    ")
+        out += ["#pragma unroll", f"{ind}    for (int v = 0; v < V; ++v) {{ " + " ".join(fast) + " }", f"{ind}}} else {{"]
+        out += [f"{ind}    int m[V]; xgb::ld_mask_flagged<V>(p.m_{gname}, fl, lin, m);"]
+        out += windows(prefix, pitch, ind + "    ")
+        out += ["#pragma unroll", f"{ind}    for (int v = 0; v < V; ++v) {{ val[v] = T(0); " + " ".join(slow) + " }", f"{ind}}}"]
+        return out
+
+    d0s = sorted({k[0] for k in win} | {0})
+    name = kernel_name(g, VARIANT_TILED2, V)
+    nv1 = c["RPM"] * (c["WPM"] // V)
+    nv2 = c["TJ"] * (c["W"] // V)
+    NT = c["NCW"] * 32
+    L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    L.append(f"    constexpr int V = {V}, NCW = {c['NCW']}, NT = NCW * 32, TJ = {c['TJ']}, W = {c['W']}, HJ = {c['HJ']}, HKM = {c['HKM']}, "
+             f"HK0 = {c['HK0']}, WPM = {c['WPM']}, WP0 = {c['WP0']}, RPM = {c['RPM']}, RP0 = {c['RP0']}, NS = {c['NS']}, MR = {c['MR']}, "
+             f"DMIN = {c['DMIN']}, DMAX = {c['DMAX']}, DSPAN = DMAX - DMIN, NV1 = {nv1}, NV2 = {nv2}, "
+             f"NIT1 = {-(-nv1 // NT)}, NIT2 = {-(-nv2 // NT)};")
+    L.append(f"    typedef {T} T;")
+    L.append("    extern __shared__ __align__(128) unsigned char xgb_smem[];")
+    L.append("    uint64_t *full = reinterpret_cast<uint64_t *>(xgb_smem);")
+    L.append("    uint64_t *empty = full + NS;")
+    L.append("    T *stages = reinterpret_cast<T *>(xgb_smem + 256);        // [NS][RP0][WP0] input planes (u^n)")
+    L.append("    T *mids = stages + NS * RP0 * WP0;                        // [MR][RPM][WPM] middle planes (u^{n+1})")
+    L.append("    const T *src = static_cast<const T *>(p.aux0);")
+    L.append("    T *out2 = static_cast<T *>(p.aux1), *out1 = static_cast<T *>(p.aux2);")
+    L.append("    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+    L.append("    const int64_t c0 = (int64_t)blockIdx.x * W, j0 = (int64_t)blockIdx.y * TJ;")
+    L.append("    const int64_t i0 = p.r_lo + (int64_t)blockIdx.z * p.chunk0;")
+    L.append("    if (i0 >= p.r_hi) return;")
+    L.append("    const int64_t iend = (i0 + p.chunk0 < p.r_hi) ? (i0 + p.chunk0) : p.r_hi;")
+    L.append("    const int64_t S1 = p.n2, S0 = p.n1 * p.n2, total = p.n0 * S0;")
+    L.append("    const int nplanes = (int)(iend - i0) + 2 * DSPAN;            // input planes this CTA streams")
+    L.append("    if (threadIdx.x == 0) {")
+    L.append("        for (int s = 0; s < NS; ++s) { xgb::pipe::mbar_init(&full[s], 1); xgb::pipe::mbar_init(&empty[s], NCW); }")
+    L.append("        xgb::pipe::fence_barrier_init();")
+    L.append("    }")
+    L.append("    __syncthreads();")
+    L.append("    if (warp == NCW) {                                         // producer: RP0 row copies per input plane")
+    L.append("        int s = 0, eph = 1;")
+    L.append("        const T *plane = src + ((i0 + 2 * DMIN) * S0 + (j0 - 2 * HJ) * S1 + (c0 - HK0));")
+    L.append("        for (int t = 0; t < nplanes; ++t, ++s, plane += S0) {")
+    L.append("            if (s == NS) { s = 0; eph ^= 1; }")
+    L.append("            if (t >= NS) xgb::pipe::mbar_wait(&empty[s], eph);")
+    L.append("            if (lane == 0) xgb::pipe::mbar_expect_tx(&full[s], (uint32_t)(RP0 * WP0 * sizeof(T)));")
+    L.append("            __syncwarp();")
+    L.append("            for (int jj = lane; jj < RP0; jj += 32)")
+    L.append("                xgb::pipe::bulk_g2s(stages + ((int64_t)s * RP0 + jj) * WP0, plane + jj * S1, (uint32_t)(WP0 * sizeof(T)), &full[s]);")
+    L.append("        }")
+    L.append("        return;")
+    L.append("    }")
+    L.extend(hoist_lines(hoist))
+    L.append("    const int tid = warp * 32 + lane;")
+    L.append("    int fs = 0, fph = 0, rs = 0, ms = 0;")
+    L.append("    int64_t lin_mid = (i0 + DMIN) * S0 + (j0 - HJ) * S1 + (c0 - HKM);   // first cell of the next middle plane's region")
+    L.append("    int64_t lin_out = i0 * S0 + j0 * S1 + c0;")
+    L.append("    for (int t = 0; t < nplanes; ++t) {")
+    L.append("        xgb::pipe::mbar_wait(&full[fs], fph);")
+    L.append("        if (t >= DSPAN) {")
+    L.append("            // ---- step 1: middle plane over rows [j0 - HJ, j0 + TJ + HJ) x columns [c0 - HKM, c0 + W + HKM)")
+    for d0 in d0s:
+        k = c["DMAX"] - d0
+        L.append(f"            const T *in{d0 - c['DMIN']} = stages + (int64_t)((fs >= {k}) ? (fs - {k}) : (fs - {k} + NS)) * (RP0 * WP0) + HJ * WP0 + (HK0 - HKM);")
+    L.append("            T *mpl = mids + (int64_t)ms * (RPM * WPM);")
+    L.append("            int fls[NIT1];")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT1; ++i) {")
+    L.append("                const int idx = tid + i * NT;")
+    L.append("                const int jj = idx / (WPM / V), kk = (idx % (WPM / V)) * V;")
+    L.append("                const int64_t lin = lin_mid + jj * S1 + kk;")
+    L.append("                fls[i] = -1;")
+    L.append(f"                if (idx < NV1 && lin >= 0 && lin + V <= total) fls[i] = xgb::ld_flag(p.m_{gname}, p.f_{gname}, lin);")
+    L.append("            }")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT1; ++i) {")
+    L.append("                const int idx = tid + i * NT;")
+    L.append("                if (idx < NV1) {")
+    L.append("                    const int jj = idx / (WPM / V), kk = (idx % (WPM / V)) * V;")
+    L.append("                    const int fl = fls[i];")
+    L.append("                    const int64_t lin = lin_mid + jj * S1 + kk;")
+    L.append("                    if (fl >= 0) {")
+    L.extend(body("in", "WP0", "                        "))
+    L.append("                        xgb::st_vec<T, V>(mpl + jj * WPM + kk, val);")
+    L.append("                    } else {")
+    L.append("                        T z[V];")
+    L.append("#pragma unroll")
+    L.append("                        for (int v = 0; v < V; ++v) z[v] = T(0);")
+    L.append("                        xgb::st_vec<T, V>(mpl + jj * WPM + kk, z);")
+    L.append("                    }")
+    L.append("                }")
+    L.append("            }")
+    L.append("            lin_mid += S0;")
+    L.append("            asm volatile(\"bar.sync 1, %0;\" :: \"n\"(NT) : \"memory\");")
+    L.append("        }")
+    L.append("        if (t >= 2 * DSPAN) {")
+    L.append("            // ---- step 2: output plane over the CTA's own TJ x W tile")
+    for d0 in d0s:
+        k = c["DMAX"] - d0
+        L.append(f"            const T *md{d0 - c['DMIN']} = mids + (int64_t)((ms >= {k}) ? (ms - {k}) : (ms - {k} + MR)) * (RPM * WPM) + HJ * WPM + HKM;")
+    L.append("            int fls[NIT2];")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT2; ++i) {")
+    L.append("                const int idx = tid + i * NT;")
+    L.append("                const int jj = idx / (W / V), kk = (idx % (W / V)) * V;")
+    L.append("                fls[i] = -1;")
+    L.append(f"                if (idx < NV2 && j0 + jj < p.n1 && c0 + kk < p.n2) fls[i] = xgb::ld_flag(p.m_{gname}, p.f_{gname}, lin_out + jj * S1 + kk);")
+    L.append("            }")
+    L.append("#pragma unroll")
+    L.append("            for (int i = 0; i < NIT2; ++i) {")
+    L.append("                const int idx = tid + i * NT;")
+    L.append("                const int fl = fls[i];")
+    L.append("                if (fl >= 0) {")
+    L.append("                    const int jj = idx / (W / V), kk = (idx % (W / V)) * V;")
+    L.append("                    const int64_t lin = lin_out + jj * S1 + kk;")
+    L.extend(body("md", "WPM", "                    "))
+    L.append("                    xgb::st_vec<T, V>(out2 + lin, val);")
+    L.append("                    if (p.opt0) {")
+    L.append(f"                        T mv[V]; xgb::ld_vec<T, V>(md{0 - c['DMIN']} + jj * WPM + kk, mv); xgb::st_vec<T, V>(out1 + lin, mv);")
+    L.append("                    }")
+    L.append("                }")
+    L.append("            }")
+    L.append("            lin_out += S0;")
+    L.append("        }")
+    L.append("        if (t >= DSPAN) {")
     L.append("            __syncwarp();")
     L.append("            if (lane == 0) xgb::pipe::mbar_arrive(&empty[rs]);")
     L.append("            rs = (rs + 1 == NS) ? 0 : rs + 1;")

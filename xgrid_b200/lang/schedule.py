@@ -495,8 +495,10 @@ class Program:
                 defer = getattr(grid, "size", 0) >= MULTISTEP_MIN_POINTS and grid.dimension == 1
             else:
                 t2 = self.groups[0].tiled2
-                defer = (getattr(grid, "dimension", 0) == 2 and not grid.sharded and TILED2_ENABLED
-                         and grid.shape[1] >= t2["W"] and grid.shape[1] % t2["V"] == 0 and grid.shape[0] >= 64)
+                nd = getattr(grid, "dimension", 0)
+                defer = (nd == self.groups[0].ndim and not grid.sharded and TILED2_ENABLED
+                         and grid.shape[-1] >= t2["W"] and grid.shape[-1] % t2["V"] == 0 and grid.shape[0] >= 64
+                         and (nd == 2 or grid.shape[1] >= t2["TJ"]))
             if defer:
                 key = tuple(a for n, a in enumerate(args) if n != self._grid_pos)
                 p = _PENDING
@@ -620,8 +622,10 @@ class Program:
         if passes:
             fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_TILED2, cfg["V"]), cfg["smem"])
             P = g.params_cls()
-            n0, cols = grid.shape
-            P.n0, P.n1, P.rows, P.cols = n0, cols, n0, cols
+            n0, cols = grid.shape[0], grid.shape[-1]
+            for a, n in enumerate(grid.shape):
+                setattr(P, f"n{a}", n)
+            P.rows, P.cols = grid.size // cols, cols
             P.r_lo, P.r_hi = 0, n0
             gname = g.slots[0].grid
             setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
@@ -631,12 +635,16 @@ class Program:
             for name, t in g.scalars.items():
                 setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
             gx = (cols + cfg["W"] - 1) // cfg["W"]
-            want = max(1, -(-TUNE["min_ctas"] // gx))
+            gj = 1 if grid.dimension == 2 else (grid.shape[1] + cfg["TJ"] - 1) // cfg["TJ"]
+            want = max(1, -(-TUNE["min_ctas"] // (gx * gj)))
             chunk0 = max(64, -(-n0 // want))
             chunks = (n0 + chunk0 - 1) // chunk0
-            gy = min(chunks, 65535)
             P.chunk0 = chunk0
-            geometry = ((gx, gy, (chunks + gy - 1) // gy), (cfg["threads"], 1, 1))
+            if grid.dimension == 2:
+                gy = min(chunks, 65535)
+                geometry = ((gx, gy, (chunks + gy - 1) // gy), (cfg["threads"], 1, 1))
+            else:
+                geometry = ((gx, gj, chunks), (cfg["threads"], 1, 1))
             for pi in range(passes):
                 x0, x1 = grid._ring[0], grid._ring[1]
                 last = pi == passes - 1
@@ -664,7 +672,7 @@ class Program:
         multi-step kernel advances T time steps: it reads the two ring levels, iterates in
         shared memory and writes the two newest levels into spare buffers that then become
         the ring (T is even, so the ring order equals the order after T single ticks)."""
-        if grid.dimension == 2:
+        if grid.dimension >= 2:
             return self._run_batch2(args, grid, count)
         g = self.groups[0]
         cfg = g.multistep
