@@ -12,7 +12,7 @@ import pytest
 import xgrid_b200 as xgrid
 from xgrid_b200 import workloads as W
 from xgrid_b200.lang import ir
-from xgrid_b200.lang.schedule import Program, HostEval, call_scalar_operator
+from xgrid_b200.lang.schedule import Program
 
 TEMP = 10
 
@@ -197,7 +197,6 @@ def test_ptr_arguments():
 
 
 def test_every_workload_compiles_for_sm100a():
-    from xgrid_b200.runtime import shim
     for name, op in W.make_kernels().items():
         prog = Program(op)
         if not prog.groups:

@@ -42,7 +42,6 @@ class Configuration:
     device: int = 0
     distributed: bool = False
     graphs: bool = True
-    strategy: str = "auto"
     temporal: bool = True
 
     def __repr__(self) -> str:
@@ -79,7 +78,7 @@ def init(*, parallel: bool = True, cc: list[str] = ["gcc", "clang"], cacheroot: 
          comment: bool = False, overstep: Literal["none", "limit", "wrap"] = "none",
          opt_level: Literal[0, 1, 2, 3] = 2, precision: Literal["float", "double"] = "float",
          validate: bool = True, device: int | None = None, distributed: bool = False,
-         graphs: bool = True, strategy: str = "auto", temporal: bool = True) -> None:
+         graphs: bool = True, temporal: bool = True) -> None:
     global _config, _epoch
     if sys.version_info < (3, 10):
         _log.fail(f"Minimum Python 3.10 is required, current version is {sys.version_info}")
@@ -90,6 +89,6 @@ def init(*, parallel: bool = True, cc: list[str] = ["gcc", "clang"], cacheroot: 
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     _config = Configuration(parallel, list(cc), cacheroot, comment, overstep, opt_level, precision,
-                            validate, device, distributed, graphs, strategy, temporal)
+                            validate, device, distributed, graphs, temporal)
     _epoch += 1
     _log.info(f"initialized with configuration: {_config}")

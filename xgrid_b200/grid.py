@@ -21,12 +21,11 @@ Public surface and ring semantics follow the reference
 from __future__ import annotations
 
 import ctypes
-import math
 
 import numpy as np
 
 from .log import Logger
-from .types import Boolean, Floating, Grid as GridT, Integer, Structure, Value, parse_annotation
+from .types import Grid as GridT, Structure, Value, parse_annotation
 
 _schedule = None
 

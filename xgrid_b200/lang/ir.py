@@ -13,7 +13,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Any, Optional
 
-from ..types import BaseType, Grid as GridT
+from ..types import BaseType
 
 
 @dataclass(frozen=True)

@@ -7,7 +7,6 @@ cached instead of rebuilt every call.
 """
 from __future__ import annotations
 
-import ctypes
 import os
 from dataclasses import astuple
 
@@ -248,6 +247,3 @@ class Launcher:
         stale = dist.HaloPlan.stale(reads)
         if stale:
             dist.transport().exchange(stale)
-
-    def finish(self) -> None:
-        pass

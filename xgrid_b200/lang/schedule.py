@@ -21,17 +21,16 @@ identities) into a CUDA graph and replayed afterwards.
 """
 from __future__ import annotations
 
-import ctypes
 import hashlib
 import math
 import os
-from dataclasses import astuple, fields as dc_fields, is_dataclass
+from dataclasses import astuple, is_dataclass
 
 import numpy as np
 
 from ..config import get_config
 from ..log import Logger
-from ..types import Boolean, Floating, Grid as GridT, Integer, Number, Pointer, Structure, Void
+from ..types import Boolean, Floating, Grid as GridT, Integer, Pointer, Structure, Void
 from . import cudagen, ir
 
 _TEMPLATE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "templates")
@@ -572,7 +571,6 @@ class Program:
         finally:
             if record:
                 graph, nodes = rt.graph_end()
-        launcher.finish()
         rtype = self.ir.signature.return_type
         if isinstance(rtype, Void) or result is None:
             result = None
