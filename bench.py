@@ -165,9 +165,13 @@ def oracle_stepper(name: str, grids, scalars):
 
 
 def cpu_arm(name: str, shape, budget_s: float, max_steps: int, sample_shape=None):
-    """Time the CPU port (oracle/xgrid_oracle.c, gcc -O3 -fopenmp, all host threads)
-    on a bounded sample of the workload.  Returns (Gpt/s, seconds per step, steps, shape)."""
+    """Time the reference's CPU implementation of the path, all host threads, on a bounded
+    sample of the workload: the reference's OWN compiled kernels (oracle/_ref, built by
+    oracle/make_ref.py from the unmodified reference; kind "reference") where they exist and
+    are valid (1-D, square 2-D), else the C port (oracle/xgrid_oracle.c, gcc -O3 -fopenmp;
+    kind "port").  Returns (Gpt/s, seconds per step, steps, shape, kind, description)."""
     import oracle
+    from oracle import ref
     shape = tuple(sample_shape or shape)
     inputs, scalars = build_inputs(name, shape)
     grids = []
@@ -176,7 +180,16 @@ def cpu_arm(name: str, shape, budget_s: float, max_steps: int, sample_shape=None
         g.now[...] = ic
         g.boundary[...] = mask
         grids.append(g)
-    step = oracle_stepper(name, grids, scalars)
+    rk = ref.KERNEL_OF.get(name)
+    use_ref = (rk is not None and ref.available(rk) and os.environ.get("XGB_CPU_ARM", "reference") != "port"
+               and (len(shape) == 1 or (len(shape) == 2 and shape[0] == shape[1])))
+    if use_ref:
+        step = lambda: ref.call(rk, *grids, *scalars)      # noqa: E731
+        kind = "reference"
+        desc = f"oracle/_ref ({ref.manifest()['_meta']['cc'].lstrip('/').strip()}: the reference's generated C)"
+    else:
+        step = oracle_stepper(name, grids, scalars)
+        kind, desc = "port", "oracle/xgrid_oracle.c gcc -O3 -fopenmp"
     step()                                   # warm-up: first touch of the second ring level
     t0 = time.perf_counter()
     step()
@@ -187,7 +200,7 @@ def cpu_arm(name: str, shape, budget_s: float, max_steps: int, sample_shape=None
         step()
     dt = time.perf_counter() - t0
     pts = float(np.prod(shape)) * WORKLOADS[name]["stmts"]
-    return pts * steps / dt / 1e9, dt / steps, steps, shape
+    return pts * steps / dt / 1e9, dt / steps, steps, shape, kind, desc
 
 
 # --------------------------------------------------------------------------- our arm
@@ -408,8 +421,9 @@ def main():
     spec = WORKLOADS[args.workload]
 
     if args.impl == "reference":
-        # the reference's CPU implementation of the path = the oracle port (the Python reference
-        # cannot travel to the GPU box); rank 0 only.
+        # the reference's CPU implementation of the path: its own generated + compiled kernels
+        # (oracle/_ref; the Python front end cannot travel to the GPU box, its output can), else
+        # the oracle port; rank 0 only.
         if rank != 0:
             return
         import oracle
@@ -417,8 +431,8 @@ def main():
         sample = shape if args.workload != "heat3d" else (64, 2048, 2048)
         K = args.steps if args.steps is not None else 10
         Wm = args.warmup if args.warmup is not None else 1
-        gpts, sec, steps, sshape = cpu_arm(args.workload, shape, budget_s=1e9, max_steps=max(1, K),
-                                           sample_shape=sample)
+        gpts, sec, steps, sshape, kind, desc = cpu_arm(args.workload, shape, budget_s=1e9, max_steps=max(1, K),
+                                                       sample_shape=sample)
         line = {"metric": "stencil Gpoint-updates/s", "value": gpts, "unit": "Gpoint-updates/s",
                 "n_gpus": max(world, args.gpus), "steps": steps, "warmup": Wm, "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -426,9 +440,9 @@ def main():
                 "config": {"workload": f"{args.workload} {'x'.join(map(str, shape))} fp64",
                            "kernel": spec["kernel"]},
                 "cpu_baseline": {"value": gpts, "unit": "Gpoint-updates/s", "cores": oracle.threads(),
-                                 "kind": "port",
+                                 "kind": kind,
                                  "sample": f"{steps} steps of {args.workload} at {'x'.join(map(str, sshape))}, "
-                                           "oracle/xgrid_oracle.c gcc -O3 -fopenmp"},
+                                           + desc},
                 "e2e": {"value": gpts, "unit": "Gpoint-updates/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
@@ -445,11 +459,12 @@ def main():
             import oracle
             shape = tuple(args.shape) if args.shape else spec["shape"]
             sample = shape if args.workload != "heat3d" else (64, 2048, 2048)
-            gpts, sec, steps, sshape = cpu_arm(args.workload, shape, args.cpu_budget, 200, sample_shape=sample)
+            gpts, sec, steps, sshape, kind, desc = cpu_arm(args.workload, shape, args.cpu_budget, 200,
+                                                           sample_shape=sample)
             line["cpu_baseline"] = {"value": gpts, "unit": "Gpoint-updates/s", "cores": oracle.threads(),
-                                    "kind": "port",
+                                    "kind": kind,
                                     "sample": f"{steps} steps of {args.workload} at {'x'.join(map(str, sshape))} "
-                                              f"({sec * 1e3:.2f} ms/step), oracle/xgrid_oracle.c gcc -O3 -fopenmp"}
+                                              f"({sec * 1e3:.2f} ms/step), " + desc}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

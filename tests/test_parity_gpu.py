@@ -623,3 +623,48 @@ def test_tiled2_3d_matches_step_at_a_time(tmp_path, monkeypatch, shape, calls):
     eq(u._data[0], h._data[0], "L0")
     eq(u._data[1], h._data[1], "L1")
     assert STATS.get("tiled2", 0) == before + calls // 2
+
+
+# --------------------------------------------------------------------------- vs the reference's own compiled kernels
+@pytest.mark.parametrize("case", ["conv1d", "diff2d", "conv2d", "cavity"])
+def test_against_reference_compiled_kernels(k64, case):
+    """CUDA path vs oracle/_ref (the unmodified reference's generated C, compiled by the reference
+    itself in the build container -- oracle/make_ref.py), same seeded inputs, every ring level."""
+    from oracle import ref
+    if not ref.available(ref.KERNEL_OF[case]):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(21)
+    if case == "conv1d":
+        n = 1 << 20
+        ic, dx = W.ic_1d(n)
+        ic = ic + 0.1 * rng.random(n)
+        mask = np.zeros(n, np.int32)
+        mask[0] = 1
+        setups, scalars, steps = [((n,), ic, mask)], (1.0, 0.5 * dx, dx), 130
+    elif case in ("diff2d", "conv2d"):
+        n = 1536
+        ic = rng.random((n, n))
+        setups = [((n, n), ic, W.shell_mask((n, n)))]
+        scalars, steps = ((0.2,), 7) if case == "diff2d" else ((1.0, 0.0003, 0.0013, 0.0013), 7)
+    else:
+        n = 384
+        masks = W.cavity_masks(n, n)
+        ics = [np.zeros((n, n)), np.zeros((n, n)), 0.01 * rng.random((n, n)), 0.01 * rng.random((n, n))]
+        setups = [((n, n), ic, m) for ic, m in zip(ics, masks)]
+        scalars = (W.Config(1.0, 0.1, 1e-4 * (100.0 / (n - 1)) ** 2, 2.0 / (n - 1), 2.0 / (n - 1)),)
+        steps = 3
+    dev, host = [], []
+    for shape, ic, mask in setups:
+        dev.append(make_grid(ic, mask))
+        h = HostGrid(shape)
+        h.now[...] = ic
+        h.boundary[...] = mask
+        host.append(h)
+    kern = k64[ref.KERNEL_OF[case]]
+    for _ in range(steps):
+        kern(*dev, *scalars)
+        ref.call(ref.KERNEL_OF[case], *host, *scalars)
+    for d, h in zip(dev, host):
+        assert len(d._data) == len(h._data)
+        for k, (x, y) in enumerate(zip(d._data, h._data)):
+            eq(x, y, f"{case} level {k}")
