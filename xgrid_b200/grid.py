@@ -108,6 +108,7 @@ class Grid:
         self._mask_any = False
         self._lists: dict = {}          # mask value -> (device ptr, count)
         self._mask_version = 0
+        self._pair_ok: dict = {}        # (pair id, mask version) -> fused-pair eligibility (lang/jacobi2.py)
         self._mask_hist = None
         self._ghost = 1                 # zero rows on both sides of axis 0
         self._allocs: list[int] = []    # raw device allocations to free

@@ -13,7 +13,7 @@ from dataclasses import astuple
 import numpy as np
 
 from ..types import Pointer, Structure
-from . import cudagen
+from . import cudagen, jacobi2
 
 SPARSE_FRACTION = 16      # run a mask!=0 statement over its index list when it
                           # covers less than 1/16 of the grid
@@ -120,7 +120,51 @@ class Launcher:
             return t.ctype(*astuple(raw))
         return raw.item() if isinstance(raw, np.generic) else raw
 
-    def __call__(self, g: cudagen.Group, env: dict) -> None:
+    # ---- two solver iterations per pass (lang/jacobi2.py)
+    def pair_ok(self, pair) -> bool:
+        """Dynamic eligibility of the fused sweep-boundary-sweep pass for this call's grids."""
+        g = pair.sweep
+        lead = self.grids[g.lead]
+        c = pair.config
+        if lead.sharded or lead.dimension != 2:
+            return False
+        n0, cols = lead.shape
+        if cols % c["V"] or cols < jacobi2.MIN_COLS or n0 < jacobi2.MIN_ROWS:
+            return False
+        if any(self.grids[s.grid].shape != lead.shape for s in g.slots):
+            return False
+        if not lead._mask_any:
+            return True
+        key = (id(pair), lead._mask_version)
+        ok = lead._pair_ok.get(key)
+        if ok is None:
+            if len(lead._pair_ok) > 16:
+                lead._pair_ok.clear()
+            ok = lead._pair_ok[key] = jacobi2.chains_fit(pair, lead._mask_snapshot)
+        return ok
+
+    def run_pair(self, pair, env: dict) -> None:
+        g, c = pair.sweep, pair.config
+        lead = self.grids[g.lead]
+        P = self._params(g, env)
+        n0, cols = lead.shape
+        gx = (cols + c["W"] - 1) // c["W"]
+        want = max(1, -(-TUNE["min_ctas"] // gx))
+        chunk0 = jacobi2.CHUNK0 or max(32, -(-n0 // want))     # measured: 32 beats 64 / 128 (tail effect)
+        chunks = (n0 + chunk0 - 1) // chunk0
+        P.chunk0, P.r_lo, P.r_hi = chunk0, 0, n0
+        gy = min(chunks, 65535)
+        fn = self.program.function(cudagen.kernel_name(g, jacobi2.VARIANT, c["V"]), c["smem"])
+        self.rt.launch(fn, (gx, gy, (chunks + gy - 1) // gy), (c["threads"], 1, 1), P, smem=c["smem"])
+        self.launches += 1
+        STATS[jacobi2.VARIANT] = STATS.get(jacobi2.VARIANT, 0) + 1
+        self._mark_written(g)
+        lead._swap_scratch()
+        for r in pair.rules:                 # boundary statements of the second iteration
+            self(r.group, env)
+
+    def _params(self, g: cudagen.Group, env: dict):
+        """Parameter struct of a group: level pointers, masks, extents, user scalars."""
         lead = self.grids[g.lead]
         P = g.params_cls()
         for s in g.slots:
@@ -151,7 +195,14 @@ class Launcher:
                 arr[a] = n
         for name, t in g.scalars.items():
             setattr(P, f"u_{name}", self._scalar_value(t, env[name]))
+        return P
 
+    def __call__(self, g: cudagen.Group, env: dict) -> None:
+        lead = self.grids[g.lead]
+        P = self._params(g, env)
+        shape = lead.shape
+        cols = shape[-1]
+        rows = lead.size // cols if cols else 0
         if lead.size == 0:
             return
         variant, V, smem = cudagen.VARIANT_DENSE, 1, 0

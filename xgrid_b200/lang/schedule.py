@@ -31,7 +31,7 @@ import numpy as np
 from ..config import get_config
 from ..log import Logger
 from ..types import Boolean, Floating, Grid as GridT, Integer, Pointer, Structure, Void
-from . import cudagen, ir
+from . import cudagen, ir, jacobi2
 
 _TEMPLATE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "templates")
 
@@ -274,9 +274,10 @@ def call_scalar_operator(op, args, grids):
 
 
 class _Interpreter:
-    def __init__(self, definition, env, grids, launcher) -> None:
+    def __init__(self, definition, env, grids, launcher, pairs=None) -> None:
         self.d, self.env, self.grids, self.launcher = definition, env, grids, launcher
         self.ev = HostEval(env, grids)
+        self.pairs = pairs or {}        # id(ir.For) -> jacobi2.Pair (two iterations per pass)
 
     def run(self, plan):
         try:
@@ -309,7 +310,21 @@ class _Interpreter:
                 s = node[1]
                 name, t = s.variable.name, s.variable.type
                 self.env[name] = coerce(t, self.ev(s.start))
+                pair = self.pairs.get(id(s))
+                if pair is not None and not self.launcher.pair_ok(pair):
+                    pair = None
                 while bool(self.env[name] < self.ev(s.end)):
+                    if pair is not None:
+                        # at least two iterations left: sweep, boundary statements, sweep in ONE pass
+                        # (jacobi2), then the boundary statements of the second iteration
+                        with np.errstate(all="ignore"):
+                            step = self.ev(s.step)
+                            nxt = coerce(t, self.env[name] + step)
+                        if step > 0 and bool(nxt < self.ev(s.end)):
+                            self.launcher.run_pair(pair, self.env)
+                            with np.errstate(all="ignore"):
+                                self.env[name] = coerce(t, nxt + step)
+                            continue
                     try:
                         self.block(node[2])
                     except _Break:
@@ -405,7 +420,15 @@ class Program:
         for g in self.groups:
             g.name = f"xg_{tag}_g{g.gid}"
             cudagen.analyse_group(g, scope_types)
+        # solver loops whose body is [implicit sweep, boundary statements...]: two iterations per pass
+        self.pairs: dict = {}
+        if self.config.overstep == "none":
+            self._match_pairs(self.plan)
+        for g in self.groups:
             cudagen.emit_group(g, self.module_builder, scope_types, self.grid_ndims)
+        for pair in self.pairs.values():
+            jacobi2.configure(pair)
+            self.module_builder.kernels.append(jacobi2.emit(pair, self.module_builder))
         self.source = self.module_builder.source() if self.groups else ""
         self._module = None
         self._functions: dict = {}
@@ -441,6 +464,27 @@ class Program:
         self.cacheable = not any(
             isinstance(st, ir.Assignment) and isinstance(st.terminal, ir.Identifier)
             and isinstance(st.terminal.variable.type, Pointer) for st in ir.walk_stmts(self.ir.body))
+
+    def _match_pairs(self, plan: list) -> None:
+        for node in plan:
+            if isinstance(node, GroupNode):
+                continue
+            if node[0] == "for":
+                body = node[2]
+                pair = jacobi2.match(body, lambda n: n.group if isinstance(n, GroupNode) else None)
+                if pair is not None:
+                    used = set(pair.sweep.scalars)
+                    for r in pair.rules:
+                        used |= set(r.group.scalars)
+                    if node[1].variable.name not in used:      # both iterations see the same scalars
+                        self.pairs[id(node[1])] = pair
+                        continue
+                self._match_pairs(body)
+            elif node[0] == "while":
+                self._match_pairs(node[2])
+            elif node[0] == "if":
+                self._match_pairs(node[2])
+                self._match_pairs(node[3])
 
     # ---- JIT (replaces Compiler.compile's md5 cache, xgrid/util/ffi.py:67-85)
     def image(self) -> bytes:
@@ -567,7 +611,7 @@ class Program:
         if record:
             rt.graph_begin()
         try:
-            result = _Interpreter(self.ir, env, grids, launcher).run(self.plan)
+            result = _Interpreter(self.ir, env, grids, launcher, self.pairs).run(self.plan)
         finally:
             if record:
                 graph, nodes = rt.graph_end()
