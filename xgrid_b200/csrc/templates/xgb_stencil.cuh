@@ -59,6 +59,37 @@ XGB_DEV float fdiv(float x, float y) {
 XGB_DEV double fdiv(double x, float y) { return fdiv(x, (double)y); }
 XGB_DEV double fdiv(float x, double y) { return fdiv((double)x, y); }
 
+// IEEE-exact fp64 division by a divisor that does not change from point to point (dx, 2*dy,
+// dx^2+dy^2 ...): the reciprocal is rounded once per thread, every quotient then costs one
+// multiply and four FMAs instead of div.rn.f64's reciprocal seed + Newton + correction + range
+// check.  With r = RN(1/y):  q0 = RN(x r);  q1 = RN(q0 + (x - q0 y) r) is within 1/2 ulp + 2^-51 ulp
+// of x/y, i.e. a faithful quotient; one more correction step from a faithful quotient with a
+// correctly rounded reciprocal yields RN(x/y) (Markstein's theorem).  The residuals are exact
+// only while nothing underflows or overflows, so the sequence is used for 2^-900 <= |x| < 2^900
+// and 2^-100 <= |y| <= 2^100; everything else (zeros, subnormals, infinities, NaNs, extreme
+// exponents) takes the ordinary exact path.  tests/test_invdiv_gpu.py compares it with the host's
+// IEEE division over exponent sweeps, special values and adversarial divisors.
+__device__ __noinline__ double fdiv_outlined(double x, double y) { return fdiv(x, y); }   // rare path: keep call sites small
+struct InvDiv {
+    double y, r;
+    bool ok;
+    XGB_DEV explicit InvDiv(double y_) : y(y_), r(__drcp_rn(y_)) {
+        const unsigned ey = ((unsigned)__double2hiint(y_) >> 20) & 0x7ffu;
+        ok = (ey - 923u) <= 200u;                      // biased exponent 923 .. 1123  <=>  2^-100 <= |y| < 2^101
+    }
+    XGB_DEV double div(double x) const {
+        const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+        if (ok && (ex - 123u) < 1800u) {               // 2^-900 <= |x| < 2^900
+            double q = x * r;
+            double e = fma(-q, y, x);
+            q = fma(e, r, q);
+            e = fma(-q, y, x);
+            return fma(e, r, q);
+        }
+        return fdiv_outlined(x, y);
+    }
+};
+
 // --------------------------------------------------------------------------- vector access
 template <int BYTES> struct Pack;
 template <> struct Pack<1>  { typedef uint8_t  type; };

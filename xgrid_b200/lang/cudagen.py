@@ -33,6 +33,11 @@ import os as _os
 # rows loaded ahead of use per chain; 0 = off (measured: register prefetch costs occupancy, the
 # tiled variant prefetches through shared memory instead)
 MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "0"))
+# exact division by point-independent divisors through a per-thread reciprocal (xgb::InvDiv), per kernel
+# variant: it pays where a kernel is instruction-bound (the temporal-blocking variants); in the HBM-bound
+# one-pass kernels the divide is hidden anyway and the extra live registers cost more than they save
+# (measured: conv1d_nl multistep 655 -> 920 Gpoint-updates/s; cavity one-pass kernels 15.8 -> 16.7 ms)
+INVDIV_VARIANTS = set(filter(None, _os.environ.get("XGB_INVDIV", "multistep,jacobi2").split(",")))
 
 
 @dataclass
@@ -91,9 +96,11 @@ class ExprEmitter:
     """IR expression -> C text.  ``ident`` maps a scalar variable to its C
     spelling; ``tap`` maps a Stencil load to its C spelling."""
 
-    def __init__(self, module: "ModuleBuilder", ident, tap=None, hoist: dict | None = None) -> None:
+    def __init__(self, module: "ModuleBuilder", ident, tap=None, hoist: dict | None = None,
+                 variant: str = "") -> None:
         self.module, self.ident, self.tap = module, ident, tap
         self.hoist = hoist          # C text -> name of a kernel-prologue constant (None = off)
+        self.invdiv = variant in INVDIV_VARIANTS
 
     def __call__(self, e) -> str:
         text = getattr(self, "x_" + type(e).__name__)(e)
@@ -128,6 +135,15 @@ class ExprEmitter:
                 return f"xgb::sq<{ctype}>({base})"
             return f"{'pow' if wide else 'powf'}({base}, {self(e.right)})"
         if e.operator == "/" and isinstance(e.left.type, Floating) and self.tap is not None:
+            if (self.invdiv and self.hoist is not None and _invariant(e.right) and not _invariant(e.left)
+                    and all(isinstance(t, Floating) and t.width_bits == 64 for t in (e.left.type, e.right.type))):
+                # point-independent divisor: reciprocal once per thread, exact quotient per point
+                divisor = self(e.right)
+                text = f"xgb::InvDiv({divisor})"
+                name = self.hoist.get(text)
+                if name is None:
+                    name = self.hoist[text] = f"h{len(self.hoist)}"
+                return f"{name}.div({self(e.left)})"
             return f"xgb::fdiv({self(e.left)}, {self(e.right)})"     # exact; see xgb_stencil.cuh
         return f"({self(e.left)} {e.operator} {self(e.right)})"
 
@@ -876,7 +892,7 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     fast_body: list = []
     slow_body: list = []
     hoist: dict = {}
-    emit = ExprEmitter(module, _ident, tap, hoist)
+    emit = ExprEmitter(module, _ident, tap, hoist, VARIANT_TILED)
     fast_written = []
     for a in g.stmts:
         sw = a.sweep
@@ -994,7 +1010,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
         return f"cur[XSW(q + ({e.space_offset[-1]}))]"
 
     hoist: dict = {}
-    slow_emit = ExprEmitter(module, _ident, slow_tap, hoist)
+    slow_emit = ExprEmitter(module, _ident, slow_tap, hoist, VARIANT_MULTISTEP)
     slow = [f"if (m == {a.sweep.mask}) nxt[XSW(q)] = {slow_emit(a.value)};" for a in g.stmts]
     mask0 = [a for a in g.stmts if a.sweep.mask == 0]
 
@@ -1010,7 +1026,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
         def reg_tap(e: ir.Stencil, lvl=s_ - 1) -> str:
             return f"x{lvl}[i + ({h + e.space_offset[-1]})]"
 
-        emit = ExprEmitter(module, _ident, reg_tap, hoist)
+        emit = ExprEmitter(module, _ident, reg_tap, hoist, VARIANT_MULTISTEP)
         if mask0:
             reg_lines.append(f"                x{s_}[i] = {emit(mask0[-1].value)};")
         else:
@@ -1159,7 +1175,7 @@ def _emit_tiled2(g: Group, module: ModuleBuilder, c: dict) -> str:
         lo, _ = win[e.space_offset[0]]
         return f"w{e.space_offset[0] - c['DMIN']}[v + {e.space_offset[-1] - lo}]"
 
-    emit = ExprEmitter(module, _ident, tap, hoist)
+    emit = ExprEmitter(module, _ident, tap, hoist, VARIANT_TILED2)
     slow = [f"if (m[v] == {a.sweep.mask}) val[v] = {emit(a.value)};" for a in g.stmts]
     fast = [f"val[v] = {emit(a.value)};" for a in g.stmts if a.sweep.mask == 0][-1:]
 
@@ -1366,7 +1382,7 @@ def _emit_tiled2_3d(g: Group, module: ModuleBuilder, c: dict) -> str:
         key = (e.space_offset[0], e.space_offset[1])
         return f"{wname[key]}[v + {e.space_offset[2] - win[key][0]}]"
 
-    emit = ExprEmitter(module, _ident, tap, hoist)
+    emit = ExprEmitter(module, _ident, tap, hoist, VARIANT_TILED2)
     slow = [f"if (m[v] == {a.sweep.mask}) val[v] = {emit(a.value)};" for a in g.stmts]
     fast = [f"val[v] = {emit(a.value)};" for a in g.stmts if a.sweep.mask == 0][-1:]
 

@@ -182,7 +182,7 @@ def emit(pair: Pair, module: ModuleBuilder) -> str:
         return f"x{xindex[(e.variable.name, e.level)]}[v]"
 
     hoist: dict = {}
-    rhs = ExprEmitter(module, _ident, tap, hoist)(a.value)
+    rhs = ExprEmitter(module, _ident, tap, hoist, VARIANT)(a.value)
     lo0, _ = win[0]
     centre = f"w{HA}[v + {-lo0}]"
 
