@@ -66,8 +66,8 @@ XGB_DEV double fdiv(float x, double y) { return fdiv((double)x, y); }
 // of x/y, i.e. a faithful quotient; one more correction step from a faithful quotient with a
 // correctly rounded reciprocal yields RN(x/y) (Markstein's theorem).  The residuals are exact
 // only while nothing underflows or overflows, so the sequence is used for 2^-900 <= |x| < 2^900
-// and 2^-100 <= |y| <= 2^100; everything else (zeros, subnormals, infinities, NaNs, extreme
-// exponents) takes the ordinary exact path.  tests/test_invdiv_gpu.py compares it with the host's
+// and 2^-100 <= |y| <= 2^100; zero numerators return the signed zero directly and everything else
+// (subnormals, infinities, NaNs, extreme exponents) takes the ordinary exact path, out of line.  tests/test_invdiv_gpu.py compares it with the host's
 // IEEE division over exponent sweeps, special values and adversarial divisors.
 __device__ __noinline__ double fdiv_outlined(double x, double y) { return fdiv(x, y); }   // rare path: keep call sites small
 struct InvDiv {
@@ -86,6 +86,9 @@ struct InvDiv {
             e = fma(-q, y, x);
             return fma(e, r, q);
         }
+        if (ok && x == 0.0)                            // quiescent regions of a PDE field are exactly zero
+            return __longlong_as_double((__double_as_longlong(x) ^ __double_as_longlong(y)) &
+                                        (long long)0x8000000000000000ULL);
         return fdiv_outlined(x, y);
     }
 };

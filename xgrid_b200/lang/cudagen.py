@@ -36,8 +36,8 @@ MARCH_PREFETCH = int(_os.environ.get("XGB_PF", "0"))
 # exact division by point-independent divisors through a per-thread reciprocal (xgb::InvDiv), per kernel
 # variant: it pays where a kernel is instruction-bound (the temporal-blocking variants); in the HBM-bound
 # one-pass kernels the divide is hidden anyway and the extra live registers cost more than they save
-# (measured: conv1d_nl multistep 655 -> 920 Gpoint-updates/s; cavity one-pass kernels 15.8 -> 16.7 ms)
-INVDIV_VARIANTS = set(filter(None, _os.environ.get("XGB_INVDIV", "multistep,jacobi2").split(",")))
+# (measured: conv1d_nl multistep 655 -> 956 Gpoint-updates/s; cavity with it in the one-pass / fused kernels 15.8 -> 16.1-16.3 ms)
+INVDIV_VARIANTS = set(filter(None, _os.environ.get("XGB_INVDIV", "multistep").split(",")))
 
 
 @dataclass
