@@ -723,6 +723,7 @@ TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", "0"))      # 0 = per-dimensi
 TILED_TJ = int(_os.environ.get("XGB_TJ", "8"))
 TILED_WX3 = int(_os.environ.get("XGB_WX3", "1"))       # consumer warps side by side along k in 3-D
 TILED_NSV = int(_os.environ.get("XGB_NSV", "0"))         # 0 = per-dimension default below
+TILED_WX2 = int(_os.environ.get("XGB_WX2", "0"))         # consumer warps per CTA in 2-D; 0 = by stream count
 # measured on B200 (profiles/r1_experiments.md): 2-D likes 2 vectors per thread and ~56 KB rings
 # (4 CTAs/SM); 3-D amortises the per-plane bookkeeping better with 4 vectors per thread (256-column
 # tiles) and deeper rings (2 CTAs/SM)
@@ -751,7 +752,11 @@ def tiled_config(g: Group):
             hk = max(hk, abs(off[-1]))
     hk = -(-hk // V) * V                       # keep shared rows 16-byte aligned
     if g.ndim == 2:
-        ncw, tj, wx = 8, 1, 8                  # 8 consumer warps side by side
+        # consumer warps side by side.  Measured on 8192^2 / 16384^2 fp64: kernels that stream two or more
+        # levels (cavity's pressure / velocity sweeps) run 8 % faster with 4 warps per CTA (more, smaller
+        # barrier groups per SM); the single-stream 5-point sweep is 6 % faster with 8
+        wx2 = TILED_WX2 or (4 if sum(1 for s in g.slots if s.read) >= 2 else 8)
+        ncw, tj, wx = wx2, 1, wx2
     else:
         tj, wx = TILED_TJ, TILED_WX3           # tj rows x wx warps per row
         ncw = tj * wx
@@ -1129,7 +1134,7 @@ def tiled2_config(g: Group):
     elem = g.slots[0].elem
     if isinstance(elem, (Structure, Boolean)) or elem.width_bytes != 8:
         return None
-    V, NSV, NCW = 2, 2, 8
+    V, NSV, NCW = 2, int(_os.environ.get("XGB_T2_NSV", "2")), int(_os.environ.get("XGB_T2_NCW", "4"))
     dmin = dmax = hk = 0
     for a in g.stmts:
         for ld in a.sweep.loads:

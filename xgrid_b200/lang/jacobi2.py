@@ -45,7 +45,8 @@ from .cudagen import ExprEmitter, Group, ModuleBuilder, _ident, hoist_lines, ker
 VARIANT = "jacobi2"
 ENABLED = os.environ.get("XGB_JACOBI2", "1") != "0"
 VEC = 2                                             # points per thread per row (one 16-byte vector)
-WARPS = int(os.environ.get("XGB_J2_NCW", "8"))      # consumer warps per CTA
+WARPS = int(os.environ.get("XGB_J2_NCW", "3"))      # consumer warps per CTA (measured on cavity 8192^2: 2: 16.5 ms,
+                                                    # 3: 14.6, 4: 15.0, 6: 15.4, 8: 15.8 -- small barrier groups win)
 TILE_W = int(os.environ.get("XGB_J2_W", "0"))       # output columns per CTA; 0 = middle row == one vector per thread
 STAGES = int(os.environ.get("XGB_J2_NS", "5"))
 MIN_COLS = int(os.environ.get("XGB_J2_MIN_COLS", "512"))   # narrower grids stay step-at-a-time
