@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from typing import Any, Callable
 
+from .. import config as _config
 from ..log import Logger
 from ..types import BaseType
 
@@ -68,7 +69,10 @@ class Operator:
 
     def __call__(self, *args: Any) -> Any:
         if self.mode == "kernel":
-            return self._program()(*args)
+            prog = self.native
+            if prog is None or self._epoch != _config._epoch:
+                prog = self._program()
+            return prog(*args)
         if self.mode == "function":
             return self.func(*args)
         self.logger.dead(f"Invalid call to non-kernel or non-function ({self.mode}) operator '{self.name}'")

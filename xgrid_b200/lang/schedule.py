@@ -527,6 +527,10 @@ class Program:
     # ---- call
     def __call__(self, *args):
         global _PENDING
+        p = _PENDING
+        if p is not None and p["program"] is self and p["count"] < PENDING_LIMIT and args == p["args"]:
+            p["count"] += 1         # one more identical deferred call (grids compare by identity)
+            return None
         sig = self.ir.signature.arguments
         if len(args) != len(sig):
             # xgrid/util/ffi.py:31-33
