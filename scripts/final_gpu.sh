@@ -27,7 +27,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:tile
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:multistep -s 3 -c 1 -o $O/${P}_conv1d_nl_multistep \
     python bench.py --workload conv1d_nl --steps 1000 --warmup 200 --no-cpu --no-e2e > /dev/null 2>&1
 tail -3 $O/${P}_gputests.log; cat $O/${P}_smoke.log | tail -1
-python - '$P' <<'PY'
+python - "$P" <<'PY'
 import json,sys
 for l in open("gpurun_out/%s_bench_all.jsonl" % (sys.argv[1] if len(sys.argv)>1 else "r1b")):
     l=l.strip()
