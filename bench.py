@@ -39,7 +39,7 @@ WORKLOADS = {
     "diff1d":    dict(kernel="diffusion_1d", ndim=1, shape=(1 << 24,), stmts=1, bytes_pt=16, steps=10000, warmup=200),
     "conv2d":    dict(kernel="convection_2d", ndim=2, shape=(16384, 16384), stmts=1, bytes_pt=16, steps=200, warmup=10),
     "diff2d":    dict(kernel="diffusion_2d", ndim=2, shape=(16384, 16384), stmts=1, bytes_pt=16, steps=200, warmup=10),
-    "cavity":    dict(kernel="cavity_kernel", ndim=2, shape=(8192, 8192), stmts=54, bytes_pt=1312, steps=10, warmup=3),
+    "cavity":    dict(kernel="cavity_kernel", ndim=2, shape=(8192, 8192), stmts=54, bytes_pt=1312, steps=10, warmup=5),
     "heat3d":    dict(kernel="heat_3d", ndim=3, shape=(256, 2048, 2048), stmts=1, bytes_pt=16, steps=50, warmup=5),
     "ewmul":     dict(kernel="elementwise_mul", ndim=1, shape=(10000,), stmts=1, bytes_pt=24, steps=2000, warmup=50),
 }

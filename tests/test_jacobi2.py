@@ -202,6 +202,13 @@ def test_model_matches_two_iterations(solvers):
 
 
 # --------------------------------------------------------------------------- GPU
+def fused_passes(trips: int) -> int:
+    """Fused passes per call: pairs of iterations, kept even when the trip count is even (so the number of
+    level-0 <-> scratch swaps per call stays even and the CUDA-graph arrangement repeats every 2nd call)."""
+    pairs = trips // 2
+    return pairs - 1 if (pairs % 2 == 1 and trips % 2 == 0) else pairs
+
+
 def _run_both(kernel, shape, mask, scalars, calls, with_b, seed):
     rng = np.random.default_rng(seed)
     ics = [rng.random(shape)] + ([rng.random(shape)] if with_b else [])
@@ -240,7 +247,7 @@ def test_fused_pairs_random_geometry(solvers, shape, n, obstacles, seed, clean):
     mask = shell_geometry(shape, rng, obstacles, clean)
     before = STATS.get("jacobi2", 0)
     _run_both(s5, shape, mask, (0.23, n), 3, True, seed)
-    assert STATS.get("jacobi2", 0) - before == (3 * (n // 2) if clean else 0)
+    assert STATS.get("jacobi2", 0) - before == (3 * fused_passes(n) if clean else 0)
 
 
 @pytest.mark.gpu
@@ -299,4 +306,4 @@ def test_cavity_fused(n):
         for lvl, (x, y) in enumerate(zip(g._data, h._data)):
             assert np.array_equal(x, y, equal_nan=True), f"{name} level {lvl}: {int((x != y).sum())} cells differ"
     # the first two calls run step-at-a-time launches (the second one records the CUDA graph)
-    assert STATS.get("jacobi2", 0) - before >= 25 * 2
+    assert STATS.get("jacobi2", 0) - before >= fused_passes(50) * 2

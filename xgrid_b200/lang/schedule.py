@@ -313,18 +313,27 @@ class _Interpreter:
                 pair = self.pairs.get(id(s))
                 if pair is not None and not self.launcher.pair_ok(pair):
                     pair = None
+                fused_left = 0
+                if pair is not None:
+                    # the body holds only sweeps, so the trip count is known here.  Every fused pass swaps
+                    # the iterated grid's level 0 with its scratch buffer ONCE (two single sweeps swap twice);
+                    # keep the number of swaps per call even, so that the buffer arrangement -- and with it
+                    # the recorded CUDA graph -- repeats every second call instead of every sixth
+                    with np.errstate(all="ignore"):
+                        step, lo, hi = int(self.ev(s.step)), int(self.env[name]), int(self.ev(s.end))
+                    trips = max(0, -(-(hi - lo) // step)) if step > 0 else 0
+                    fused_left = trips // 2
+                    if fused_left % 2 == 1 and trips % 2 == 0:
+                        fused_left -= 1
                 while bool(self.env[name] < self.ev(s.end)):
-                    if pair is not None:
-                        # at least two iterations left: sweep, boundary statements, sweep in ONE pass
-                        # (jacobi2), then the boundary statements of the second iteration
+                    if fused_left > 0:
+                        # sweep, boundary statements, sweep in ONE pass (jacobi2), then the boundary
+                        # statements of the second iteration
+                        fused_left -= 1
+                        self.launcher.run_pair(pair, self.env)
                         with np.errstate(all="ignore"):
-                            step = self.ev(s.step)
-                            nxt = coerce(t, self.env[name] + step)
-                        if step > 0 and bool(nxt < self.ev(s.end)):
-                            self.launcher.run_pair(pair, self.env)
-                            with np.errstate(all="ignore"):
-                                self.env[name] = coerce(t, nxt + step)
-                            continue
+                            self.env[name] = coerce(t, coerce(t, self.env[name] + step) + step)
+                        continue
                     try:
                         self.block(node[2])
                     except _Break:
