@@ -132,6 +132,11 @@ def build_inputs(name: str, shape, seed: int = 0):
         dx, dy = 2.0 / (n1 - 1), 2.0 / (n0 - 1)
         dt = 1e-4 * (100.0 / (n1 - 1)) ** 2
         z = np.zeros(shape)
+        if os.environ.get("XGB_BENCH_IC") == "random":
+            # developed-flow stand-in (diagnostic only): no field is exactly zero, so every fp64 divide
+            # takes its full path instead of the zero-numerator shortcut the quiescent zero IC allows
+            rng = np.random.default_rng(seed)
+            return [(1e-3 * rng.random(shape), m) for m in (mb, mp, mu, mv)], (W.Config(1.0, 0.1, dt, dx, dy),)
         return [(z, mb), (z, mp), (z, mu), (z, mv)], (W.Config(1.0, 0.1, dt, dx, dy),)
     if name == "ewmul":
         rng = np.random.default_rng(seed)
