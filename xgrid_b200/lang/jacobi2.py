@@ -39,7 +39,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from ..types import Boolean, Structure
-from . import cudagen, ir
+from . import ir
 from .cudagen import ExprEmitter, Group, ModuleBuilder, _ident, hoist_lines, kernel_name
 
 VARIANT = "jacobi2"
