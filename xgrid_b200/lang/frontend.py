@@ -207,9 +207,17 @@ class Parser:
         if target is lang.c:
             prev, self.in_c = self.in_c, True
             try:
-                return self.block(node.body)
+                body = self.block(node.body)
             finally:
                 self.in_c = prev
+            # the reference pastes every string into ONE C scope: consecutive strings form one block
+            merged: list = []
+            for st in body:
+                if isinstance(st, ir.Inline) and merged and isinstance(merged[-1], ir.Inline):
+                    merged[-1] = ir.Inline(merged[-1].location, merged[-1].source + "\n" + st.source)
+                else:
+                    merged.append(st)
+            return merged
         if target is lang.boundary:
             args = call.args
             if len(args) == 2:      # stale ``boundary(u, k)`` form (test.py:217) -> alias

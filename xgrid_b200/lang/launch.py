@@ -163,6 +163,31 @@ class Launcher:
         for r in pair.rules:                 # boundary statements of the second iteration
             self(r.group, env)
 
+    # ---- `with xgrid.c()` (lang/inlinec.py): the text runs as one device thread, in stream order
+    def inline(self, stmt, env: dict) -> None:
+        ik = self.program.inlines[id(stmt)]
+        P = ik.params_cls()
+        depth = self.program.depth
+        for name in ik.grids:
+            grid = self.grids[name]
+            levels = getattr(P, f"d_{name}")
+            for l in range(depth):
+                levels[l] = grid._ring[l].dev if l < len(grid._ring) else None
+            shape = getattr(P, f"shape_{name}")
+            for a, n in enumerate(grid.shape):
+                shape[a] = n
+            setattr(P, f"m_{name}", grid._mask_dev if grid._mask_any else None)
+            for lv in grid._ring:          # the text may write any level
+                lv.halo_ok = False
+                lv.halo_event = 0
+        for name, t in ik.scalars:
+            if name in env and env[name] is not None:
+                setattr(P, f"u_{name}", self._scalar_value(t, env[name]))
+        fn = self.program.function(ik.name)
+        self.rt.launch(fn, (1, 1, 1), (1, 1, 1), P)
+        self.launches += 1
+        STATS["inline"] = STATS.get("inline", 0) + 1
+
     def _params(self, g: cudagen.Group, env: dict):
         """Parameter struct of a group: level pointers, masks, extents, user scalars."""
         lead = self.grids[g.lead]

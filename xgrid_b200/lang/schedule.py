@@ -31,7 +31,7 @@ import numpy as np
 from ..config import get_config
 from ..log import Logger
 from ..types import Boolean, Floating, Grid as GridT, Integer, Pointer, Structure, Void
-from . import cudagen, ir, jacobi2
+from . import cudagen, inlinec, ir, jacobi2
 
 _TEMPLATE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc", "templates")
 
@@ -356,8 +356,9 @@ class _Interpreter:
         elif isinstance(s, ir.Evaluation):
             self.ev(s.value)
         elif isinstance(s, ir.Inline):
-            raise Exception("`with xgrid.c()` inline text is host C in the reference; the B200 backend "
-                            "cannot execute it (SURVEY.md §8f rank 2)")
+            if not hasattr(self.launcher, "inline"):
+                raise Exception("`with xgrid.c()` blocks are only supported in kernels")
+            self.launcher.inline(s, self.env)
         else:
             raise Exception(f"unsupported statement {type(s).__name__}")
 
@@ -438,7 +439,15 @@ class Program:
         for pair in self.pairs.values():
             jacobi2.configure(pair)
             self.module_builder.kernels.append(jacobi2.emit(pair, self.module_builder))
-        self.source = self.module_builder.source() if self.groups else ""
+        # `with xgrid.c()` blocks: one single-thread device kernel each (lang/inlinec.py)
+        self.inlines: dict = {}
+        for k, st in enumerate(inlinec.collect(self.ir.body)):
+            text, ik = inlinec.emit(tag, k, st, self.ir.scope, self.depth, self.module_builder)
+            if not self.inlines:
+                self.module_builder.kernels.append(inlinec.PRELUDE + "\n".join(op.macro) + "\n")
+            self.module_builder.kernels.append(text)
+            self.inlines[id(st)] = ik
+        self.source = self.module_builder.source() if (self.groups or self.inlines) else ""
         self._module = None
         self._functions: dict = {}
         # temporal blocking: the whole kernel is scalar prologue + ONE 1-D group on one grid
