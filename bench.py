@@ -54,18 +54,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The sampler is
+    started BEFORE the warm-up (nvidia-smi needs a few hundred ms to come up) and every row is time-stamped;
+    `summary()` uses the rows that fall inside [mark_start, mark_end], or the nearest ones if the timed
+    region was shorter than one sampling period."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int) -> None:
         self.device, self.rows, self.proc = device, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "25"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -75,11 +79,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.12)
+            time.sleep(0.06)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -87,12 +97,21 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        good = [(t, r) for t, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        rows = [r for t, r in good if t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if not rows and good:
+            mid = 0.5 * (t0 + min(t1, t0 + 1e9))
+            rows = [r for _, r in sorted(good, key=lambda tr: abs(tr[0] - mid))[:2]]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        sm = [float(r[0]) for r in rows]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------- workload construction
@@ -277,19 +296,21 @@ def run_ours(args, rank: int, world: int):
     points = float(np.prod(shape))
     # ---- device-resident throughput (`value`) ---------------------------------
     grids = fresh_grids()
-    for _ in range(Wm):
-        kern(*grids, *scalars)
-    rt.sync()
-    ev0, ev1 = rt.event_create(), rt.event_create()
-    barrier()
-    rt.device_sync()
-    n0 = rt.launch_count()
     with ClockSampler(local_rank) as clocks:
+        for _ in range(Wm):
+            kern(*grids, *scalars)
+        rt.sync()
+        ev0, ev1 = rt.event_create(), rt.event_create()
+        barrier()
+        rt.device_sync()
+        n0 = rt.launch_count()
+        clocks.mark_start()
         rt.event_record(ev0)
         for _ in range(K):
             kern(*grids, *scalars)
         rt.event_record(ev1)
         rt.event_sync(ev1)
+        clocks.mark_end()
     rt.device_sync()
     barrier()
     launches = rt.launch_count() - n0

@@ -227,3 +227,25 @@ def test_ring_semantics_on_host_only():
     assert len(g._ring) == 3
     g._op_invoke(1, False)
     assert len(g._ring) == 1
+
+
+def test_struct_field_store_is_rejected_like_the_reference():
+    """`g[0].x = ...`: Python gives the inner subscript a Load context, so the reference's
+    StencilParser (xgrid/lang/generator.py:56-65) dies with this very message; same here."""
+    from dataclasses import dataclass
+    xgrid.init(precision="double", cacheroot=".xgrid")
+
+    @dataclass
+    class V2:
+        x: float
+        y: float
+
+    globals()["V2"] = V2
+    g1 = xgrid.grid[V2, 1]
+
+    @xgrid.kernel()
+    def store_field(v: g1) -> None:
+        v[0].x = 1.0
+
+    with pytest.raises(Exception, match="without stencil context"):
+        Program(store_field)
