@@ -249,3 +249,26 @@ def test_struct_field_store_is_rejected_like_the_reference():
 
     with pytest.raises(Exception, match="without stencil context"):
         Program(store_field)
+
+
+def test_multistep_launch_plan():
+    """A deferred run of 1-D calls = full T-step launches + one tail launch (multiple of S, >= 2*S) + single steps;
+    every launch advances an even number of steps (ring order) and nothing is lost."""
+    from xgrid_b200.lang.schedule import multistep_launches
+    assert multistep_launches(10000 - 2 * 4096, 64, 4) == ([64] * 28 + [16], 0)
+    assert multistep_launches(20, 64, 4) == ([20], 0)
+    assert multistep_launches(70, 64, 4) == ([64], 6)            # 6 < 2*S: the remainder runs step-at-a-time
+    assert multistep_launches(7, 64, 4) == ([], 7)
+    assert multistep_launches(150, 64, 4, tail=False) == ([64, 64], 22)
+    for T, S in ((64, 4), (32, 4), (16, 2), (6, 2)):
+        for count in range(0, 200):
+            steps, left = multistep_launches(count, T, S)
+            assert sum(steps) + left == count and all(x % 2 == 0 and S * 2 <= x <= T and x % S == 0 for x in steps)
+            assert left < 2 * S + S and steps.count(T) == count // T
+
+
+def test_multistep_tail_variant_is_generated():
+    prog = Program(W.make_kernels()["convection_1d"])
+    src = prog.source
+    assert "xg_convection_1d_g0_multistep_v1(" in src and "xg_convection_1d_g0_multistep_tail_v1(" in src
+    assert "round < (int)p.opt0 / S" in src and "round < T / S" in src

@@ -273,6 +273,31 @@ def test_multistep_matches_oracle(k64, kernel, n, steps):
     eq(u._data[1], h._data[1], "L1 after host write")
 
 
+@pytest.mark.parametrize("steps", [8, 11, 20, 62, 63])
+def test_multistep_tail_lengths(k64, steps):
+    """Runs shorter than T go through the tail variant (step count passed at run time); a second run
+    continues from the ring it left behind."""
+    from xgrid_b200.lang.launch import STATS
+    n = 40000
+    ic, dx = W.ic_1d(n)
+    ic = ic + 0.01 * np.random.default_rng(steps).random(n)
+    mask = np.zeros(n, np.int32)
+    mask[0] = mask[-1] = 1
+    mask[777] = 7
+    u, h = make_grid(ic, mask), HostGrid((n,))
+    h.now[...] = ic
+    h.boundary[...] = mask
+    args = (0.01, 0.2 * dx * dx / 0.01, dx)
+    before = STATS.get("multistep", 0)
+    for rep in range(2):
+        for _ in range(steps):
+            k64["diffusion_1d"](u, *args)
+            oracle.step_diff1d(h, *args)
+        eq(u._data[0], h._data[0], f"L0 run {rep}")
+        eq(u._data[1], h._data[1], f"L1 run {rep}")
+    assert STATS.get("multistep", 0) - before == 2
+
+
 def test_multistep_changing_scalars_flushes(k64):
     n = 50000
     ic, dx = W.ic_1d(n)
@@ -301,7 +326,7 @@ def _free_host_gib():
 
 
 def test_full_size_conv1d_2p24(k64):
-    """config[1]: 2^24 points; 150 steps (2 fused 64-step launches + 22 single steps) vs the oracle."""
+    """config[1]: 2^24 points; 150 steps (2 fused 64-step launches + a 20-step tail launch + 2 single steps) vs the oracle."""
     n = 1 << 24
     ic, dx = W.ic_1d(n)
     u, h = make_grid(ic), HostGrid((n,))

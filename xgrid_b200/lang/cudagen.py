@@ -27,6 +27,7 @@ VARIANT_SPARSE = "sparse"
 VARIANT_MARCH = "march"
 VARIANT_TILED = "tiled"
 VARIANT_MULTISTEP = "multistep"
+VARIANT_MULTISTEP_TAIL = "multistep_tail"
 VARIANT_TILED2 = "tiled2"
 MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
 import os as _os
@@ -428,6 +429,7 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
             g.multistep = multistep_config(g)
             if g.multistep is not None:
                 module.kernels.append(_emit_multistep(g, module, g.multistep))
+                module.kernels.append(_emit_multistep(g, module, g.multistep, tail=True))
             g.tiled2 = tiled2_config(g)
             if g.tiled2 is not None:
                 module.kernels.append((_emit_tiled2_3d if g.ndim == 3 else _emit_tiled2)(g, module, g.tiled2))
@@ -996,8 +998,9 @@ def multistep_config(g: Group):
             "smem": 2 * (swlen + 2 * marg) * elem.width_bytes + L + 64}
 
 
-def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
-    """T steps per launch.  Two shared-memory buffers start as copies of the two ring levels
+def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False) -> str:
+    """T steps per launch (``tail``: the same kernel with the step count read from ``p.opt0`` --
+    a multiple of S below T -- for the remainder of a deferred run; the window keeps its T*h halo).  Two shared-memory buffers start as copies of the two ring levels
     (now / previous) of an L = W+2H window; every step writes the *older* buffer where a
     statement's mask matches -- exactly what T ticks + T sweeps do to the ring (unwritten points
     keep the value from two steps back) -- and the window of valid points shrinks by
@@ -1038,7 +1041,8 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
             reg_lines.append(f"                x{s_}[i] = x{s_ - 1}[i + {h}];")
         reg_lines.append("            }")
 
-    name = kernel_name(g, VARIANT_MULTISTEP, 1)
+    name = kernel_name(g, VARIANT_MULTISTEP_TAIL if tail else VARIANT_MULTISTEP, 1)
+    nsteps = "(int)p.opt0" if tail else "T"
     L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
     L.append(f"    constexpr int T = {c['T']}, S = {S}, P = {P}, PSH = {psh}, HS = {h}, H = {c['H']}, W = {c['W']}, L = {c['L']}, "
              f"PAD = {c['PAD']}, NT = {c['threads']}, V = {V};")
@@ -1075,7 +1079,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("    if (!masked) {")
     L.append("        // register path: S steps per round; b0 always receives the newest level (S is even)")
     L.append("        const int first = threadIdx.x * P;")
-    L.append("        for (int round = 0; round < T / S; ++round) {")
+    L.append(f"        for (int round = 0; round < {nsteps} / S; ++round) {{")
     L.append(f"            E x0[{N0}];")
     L.append("#pragma unroll")
     L.append(f"            for (int i = 0; i < {N0}; i += V) xgb::ld_vec<E, V>(b0 + XSW(first - S * HS + i), *reinterpret_cast<E (*)[V]>(&x0[i]));")
@@ -1093,7 +1097,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("        }")
     L.append("    } else {")
     L.append("        E *cur = b0, *nxt = b1;")
-    L.append("        for (int s = 1; s <= T; ++s) {")
+    L.append(f"        for (int s = 1; s <= {nsteps}; ++s) {{")
     L.append("            for (int q = s * HS + threadIdx.x; q < L - s * HS; q += NT) {")
     L.append("                const int m = sm[q];")
     L.extend("                " + x for x in slow)
@@ -1102,7 +1106,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("            E *t = cur; cur = nxt; nxt = t;")
     L.append("        }")
     L.append("    }")
-    L.append("    // T is even: b0 holds u^{n+T}, b1 holds u^{n+T-1}")
+    L.append("    // the step count is even: b0 holds the newest level, b1 the one before it")
     L.append("    for (int q = H + threadIdx.x * V; q < H + W; q += NT * V) {")
     L.append("        const int64_t gi = g0 + q;")
     L.append("        E a[V], b[V];")

@@ -380,7 +380,22 @@ class _Interpreter:
 _PENDING = None          # {"program", "args", "grid", "key", "count"}: identical calls not yet executed
 PENDING_LIMIT = 4096
 MULTISTEP_MIN_POINTS = int(os.environ.get("XGB_MS_MIN", "16384"))
+MULTISTEP_TAIL = os.environ.get("XGB_MS_TAIL", "1") != "0"     # remainders of a run: tail variant, not single steps
 TILED2_ENABLED = os.environ.get("XGB_TILED2", "1") != "0"
+
+
+def multistep_launches(count: int, T: int, S: int, tail: bool = True) -> tuple[list, int]:
+    """Split a run of `count` identical deferred 1-D calls into multi-step launches: full launches of
+    T steps, then ONE tail launch of the largest multiple of S that is left if that is at least 2*S
+    (S is even, so every launch advances an even number of steps and the ring order is preserved).
+    Returns (steps per launch, calls left for step-at-a-time execution)."""
+    steps = [T] * (count // T)
+    left = count % T
+    rest = left - left % S
+    if tail and rest >= 2 * S:
+        steps.append(rest)
+        left -= rest
+    return steps, left
 
 
 def flush_pending() -> None:
@@ -735,14 +750,18 @@ class Program:
         """`count` deferred identical calls.  While at least T remain, one launch of the
         multi-step kernel advances T time steps: it reads the two ring levels, iterates in
         shared memory and writes the two newest levels into spare buffers that then become
-        the ring (T is even, so the ring order equals the order after T single ticks)."""
+        the ring (T is even, so the ring order equals the order after T single ticks).  A
+        remainder of at least 2*S steps runs through the tail variant of the same kernel
+        (step count = the largest multiple of S, passed in ``opt0``); what is left after
+        that (< S calls, or a run shorter than 2*S) runs step-at-a-time."""
         if grid.dimension >= 2:
             return self._run_batch2(args, grid, count)
         g = self.groups[0]
         cfg = g.multistep
         T = cfg["T"]
+        launches, _ = multistep_launches(count, T, cfg["S"], MULTISTEP_TAIL)
         done = 0
-        if count >= T:
+        if launches:
             env, grids = self._bind(args)
             captured = []
             _Interpreter(self.ir, env, grids, lambda grp, e: captured.append(dict(e))).run(self.plan)
@@ -751,14 +770,13 @@ class Program:
             grid._extend_time(2)
             # a slab needs the neighbours' next H points of BOTH ring levels (and of the mask)
             grid._prepare_device(cfg["H"] if grid.sharded else 1)
-            fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_MULTISTEP, 1), cfg["smem"])
             P = g.params_cls()
             P.n0 = grid.shape[0]
             P.rows, P.cols = 1, grid.shape[0]
             gname = g.slots[0].grid
             setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
             setattr(P, f"f_{gname}", grid._flags_dev if grid._mask_any else None)
-            from .launch import Launcher
+            from .launch import Launcher, STATS
             marshal = Launcher(self, grids)
             for name, t in g.scalars.items():
                 setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
@@ -767,7 +785,9 @@ class Program:
                 from .. import dist
                 topo = dist.topology()
                 P.open_lo, P.open_hi = int(topo.lo_rank >= 0), int(topo.hi_rank >= 0)
-            while count - done >= T:
+            for steps in launches:
+                variant = cudagen.VARIANT_MULTISTEP if steps == T else cudagen.VARIANT_MULTISTEP_TAIL
+                fn = self.function(cudagen.kernel_name(g, variant, 1), cfg["smem"])
                 x0, x1 = grid._ring[0], grid._ring[1]
                 if grid.sharded:
                     stale = [(grid, lv, cfg["H"]) for lv in (x0, x1) if not lv.halo_ok]
@@ -775,13 +795,13 @@ class Program:
                         dist.transport().exchange(stale)
                 c, d = grid._spare_levels(2)
                 P.aux0, P.aux1, P.aux2, P.aux3 = x0.dev, x1.dev, c.dev, d.dev
+                P.opt0 = steps
                 rt.launch(fn, (blocks, 1, 1), (cfg["threads"], 1, 1), P, smem=cfg["smem"])
-                from .launch import STATS
                 STATS["multistep"] = STATS.get("multistep", 0) + 1
                 grid._ring, grid._spares = [c, d], [x0, x1]
                 c.where = d.where = "device"
                 c.halo_ok = d.halo_ok = False
-                done += T
+                done += steps
         for _ in range(count - done):
             self._call_now(args)
 
