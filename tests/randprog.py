@@ -128,3 +128,18 @@ def gen_inputs(seed: int, shape, ngrids: int):
         m[sprinkle > 0.995] = 7                     # matches no statement
         masks.append(m)
     return ics, masks
+
+
+def guard_array_ends(masks, shape, value: int = 7):
+    """The reference addresses taps linearly and reads whatever lies outside the array (undefined);
+    the backend reads ghost zeros there.  For comparisons AGAINST THE REFERENCE give every cell whose
+    taps (offsets up to +-2 per axis) could leave the array a mask value no statement matches, so that
+    no statement is evaluated there.  Row-wrapped reads inside the array stay."""
+    margin = 2
+    for extent in shape[1:]:
+        margin = margin * extent + 2
+    for m in masks:
+        flat = m.reshape(-1)
+        flat[:margin] = value
+        flat[flat.size - margin:] = value
+    return masks
