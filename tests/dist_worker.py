@@ -41,20 +41,57 @@ def exchange_host(h: HostGrid, level: int, topo, rows: int = 1):
     stride0 = h.size // n0
     start = h._pad
     reqs = []
+    # same order as xgb_halo_exchange: sends (lo, hi), then receives (hi, lo) -- with a ring of two both
+    # neighbours are the same peer and messages between a pair of ranks match in posting order
     if topo.lo_rank >= 0:
         send = torch.from_numpy(np.ascontiguousarray(arr[:rows]).reshape(-1))
-        recv = torch.empty(rows * stride0, dtype=torch.float64)
-        reqs += [dist.isend(send, topo.lo_rank), dist.irecv(recv, topo.lo_rank)]
+        reqs.append(dist.isend(send, topo.lo_rank))
     if topo.hi_rank >= 0:
         send2 = torch.from_numpy(np.ascontiguousarray(arr[n0 - rows:]).reshape(-1))
+        reqs.append(dist.isend(send2, topo.hi_rank))
+    if topo.hi_rank >= 0:
         recv2 = torch.empty(rows * stride0, dtype=torch.float64)
-        reqs += [dist.isend(send2, topo.hi_rank), dist.irecv(recv2, topo.hi_rank)]
+        reqs.append(dist.irecv(recv2, topo.hi_rank))
+    if topo.lo_rank >= 0:
+        recv = torch.empty(rows * stride0, dtype=torch.float64)
+        reqs.append(dist.irecv(recv, topo.lo_rank))
     for r in reqs:
         r.wait()
     if topo.lo_rank >= 0:
         flat[start - rows * stride0:start] = recv.numpy()
     if topo.hi_rank >= 0:
         flat[start + h.size:start + h.size + rows * stride0] = recv2.numpy()
+
+
+def open_diffusion_global(u, a, mode):
+    """NumPy restatement of workloads.diffusion_2d_open under overstep="wrap"/"limit" with per-axis
+    extents (same operand order as the kernel text, so fp64 results are bit-identical)."""
+    if mode == "wrap":
+        e, w, s, n = np.roll(u, -1, 1), np.roll(u, 1, 1), np.roll(u, -1, 0), np.roll(u, 1, 0)
+    else:
+        p = np.pad(u, 1, mode="edge")
+        e, w, s, n = p[1:-1, 2:], p[1:-1, :-2], p[2:, 1:-1], p[:-2, 1:-1]
+    return u + a * (e + w + s + n - 4.0 * u)
+
+
+def open_diffusion_slab(h: HostGrid, a, mode, topo):
+    """The same step on one slab: axis 1 is wrapped / clamped locally, axis 0 reads the ghost rows where the
+    slab has a neighbour (what the generated kernel does with open_lo / open_hi) and clamps otherwise."""
+    u = h._data[0]
+    n0, n1 = u.shape
+    flat, start = u.base, h._pad
+    ext = flat[start - n1:start + h.size + n1].reshape(n0 + 2, n1).copy()
+    if topo.lo_rank < 0:
+        ext[0] = ext[1]              # global lower end (only "limit" has one): clamp
+    if topo.hi_rank < 0:
+        ext[-1] = ext[-2]
+    mid = ext[1:-1]
+    if mode == "wrap":
+        e, w = np.roll(mid, -1, 1), np.roll(mid, 1, 1)
+    else:
+        p = np.pad(mid, ((0, 0), (1, 1)), mode="edge")
+        e, w = p[:, 2:], p[:, :-2]
+    return mid + a * (e + w + ext[2:] + ext[:-2] - 4.0 * mid)
 
 
 def main():
@@ -89,6 +126,27 @@ def main():
             oracle.step_heat3d(h, a)
         ref = oracle_global(gshape, ic, mask, steps, a)
         assert np.array_equal(h.now, ref.now[lo:hi]), "sharded oracle differs from single-domain oracle"
+        # overstep="wrap" makes the ranks a ring (rank 0's lower neighbour is the last rank), "limit" keeps
+        # the open chain and clamps at the global ends only: slab runs == single-domain restatement
+        shape2 = (22, 19)
+        ic2 = np.random.default_rng(11).random(shape2)
+        for omode in ("wrap", "limit"):
+            xgrid.init(precision="double", distributed=True, overstep=omode,
+                       cacheroot=os.environ.get("XG_CACHE", ".xgrid"))
+            topo2 = xdist.topology()
+            if omode == "wrap":
+                assert topo2.ring and (topo2.lo_rank, topo2.hi_rank) == ((rank - 1) % world, (rank + 1) % world)
+            else:
+                assert not topo2.ring and topo2.lo_rank == (rank - 1 if rank else -1)
+            lo2, hi2 = xdist.slab_range(shape2[0], rank, world)
+            h2 = HostGrid((hi2 - lo2, shape2[1]))
+            h2.now[...] = ic2[lo2:hi2]
+            want = ic2.copy()
+            for _ in range(6):
+                exchange_host(h2, 0, topo2)
+                h2.now[...] = open_diffusion_slab(h2, 0.2, omode, topo2)
+                want = open_diffusion_global(want, 0.2, omode)
+            assert np.array_equal(h2.now, want[lo2:hi2]), f"sharded overstep={omode} differs from the single domain"
         dist.barrier()
         if rank == 0:
             print("DIST_CPU_OK")
@@ -146,6 +204,30 @@ def main():
             oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
         for gg, hh in zip(gs, hs):
             ok = ok and np.array_equal(gg.now, hh.now[loc:hic]) and np.array_equal(gg._data[1], hh._data[1][loc:hic])
+        # overstep modes on slabs: ring ("wrap") / chain with clamping at the global ends ("limit");
+        # golden produced by the reference (square 32x32) and a non-square NumPy restatement
+        gold_dir = os.path.join(ROOT, "tests", "golden")
+        for omode in ("wrap", "limit"):
+            xgrid.init(precision="double", distributed=True, device=local, overstep=omode,
+                       cacheroot=os.environ.get("XG_CACHE", ".xgrid"))
+            ko = W.make_kernels()["diffusion_2d_open"]
+            gd = np.load(os.path.join(gold_dir, f"diff2d_{omode}_f64.npz"))
+            uo = xgrid.Grid(gd["u_in"].shape, float)
+            loo, hio = uo.row_range
+            uo.now[...] = gd["u_in"][loo:hio]
+            for _ in range(int(gd["steps"])):
+                ko(uo, float(gd["params"][0]))
+            ok = ok and np.array_equal(uo.now, gd["u.L0"][loo:hio]) and np.array_equal(uo._data[1], gd["u.L1"][loo:hio])
+            shape2 = (46, 70)
+            ic2 = np.random.default_rng(11).random(shape2)
+            un = xgrid.Grid(shape2, float)
+            lon, hin = un.row_range
+            un.now[...] = ic2[lon:hin]
+            want = ic2.copy()
+            for _ in range(7):
+                ko(un, 0.2)
+                want = open_diffusion_global(want, 0.2, omode)
+            ok = ok and np.array_equal(un.now, want[lon:hin])
         t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:

@@ -29,6 +29,16 @@ def test_topology_chain():
     assert not xdist.Topology(0, 1).sharded
 
 
+def test_topology_ring_for_wrap():
+    """overstep="wrap": the slabs form a ring, so rank 0's lower ghost rows are the last rows of the grid."""
+    assert [(xdist.Topology(r, 4, ring=True).lo_rank, xdist.Topology(r, 4, ring=True).hi_rank) for r in range(4)] \
+        == [(3, 1), (0, 2), (1, 3), (2, 0)]
+    two = xdist.Topology(1, 2, ring=True)
+    assert (two.lo_rank, two.hi_rank) == (0, 0)              # both neighbours are the same peer
+    one = xdist.Topology(0, 1, ring=True)
+    assert not one.ring and (one.lo_rank, one.hi_rank) == (-1, -1)      # a single rank wraps locally
+
+
 def _run(mode, nproc, tmp_path, port):
     env = dict(os.environ, XG_CACHE=str(tmp_path / "xg"), OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",

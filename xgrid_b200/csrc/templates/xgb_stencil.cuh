@@ -325,5 +325,18 @@ XGB_DEV Tile dense_tile(int64_t rows, int64_t cols) {
 // extents paired correctly (the reference pairs them wrongly off-square, F1).
 XGB_DEV int64_t clamp_idx(int64_t i, int64_t n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
 XGB_DEV int64_t wrap_idx(int64_t i, int64_t n) { i %= n; return i < 0 ? i + n : i; }
+// Axis 0 of a slab: where the slab has a neighbour on that side (`open`), an index off the end is
+// NOT clamped / wrapped locally -- it addresses the ghost rows, which hold the neighbour's rows
+// (for "wrap" the ranks form a ring, so the rows of the far end of the global grid).
+XGB_DEV int64_t clamp_idx0(int64_t i, int64_t n, int64_t open_lo, int64_t open_hi) {
+    if (i < 0) return open_lo ? i : 0;
+    if (i >= n) return open_hi ? i : n - 1;
+    return i;
+}
+XGB_DEV int64_t wrap_idx0(int64_t i, int64_t n, int64_t open_lo, int64_t open_hi) {
+    if (i < 0) return open_lo ? i : wrap_idx(i, n);
+    if (i >= n) return open_hi ? i : wrap_idx(i, n);
+    return i;
+}
 
 }  // namespace xgb

@@ -680,18 +680,21 @@ int xgb_halo_exchange(const xgb_halo_desc *descs, int n, xgb_handle stream) {
     cudaStream_t s = as_stream(stream);
     const int kChar = 0;  // ncclInt8
     XGB_NCCL(nccl.GroupStart());
-    for (int i = 0; i < n; ++i) {
+    // Sends first (lo, hi), then receives in the order (hi, lo): when both neighbours are the SAME
+    // rank (a ring of two, overstep="wrap") NCCL pairs the k-th send to a peer with the peer's k-th
+    // receive from us, and the peer's upper ghost must get our first rows, its lower ghost our last.
+    int rc = 0;
+    for (int i = 0; i < n && rc == 0; ++i) {
         const xgb_halo_desc &d = descs[i];
-        if (d.lo_rank >= 0) {
-            if (d.send_lo) XGB_NCCL(nccl.Send(d.send_lo, d.bytes, kChar, d.lo_rank, nccl.comm, s));
-            if (d.recv_lo) XGB_NCCL(nccl.Recv(d.recv_lo, d.bytes, kChar, d.lo_rank, nccl.comm, s));
-        }
-        if (d.hi_rank >= 0) {
-            if (d.send_hi) XGB_NCCL(nccl.Send(d.send_hi, d.bytes, kChar, d.hi_rank, nccl.comm, s));
-            if (d.recv_hi) XGB_NCCL(nccl.Recv(d.recv_hi, d.bytes, kChar, d.hi_rank, nccl.comm, s));
-        }
+        if (rc == 0 && d.lo_rank >= 0 && d.send_lo) rc = nccl.Send(d.send_lo, d.bytes, kChar, d.lo_rank, nccl.comm, s);
+        if (rc == 0 && d.hi_rank >= 0 && d.send_hi) rc = nccl.Send(d.send_hi, d.bytes, kChar, d.hi_rank, nccl.comm, s);
+        if (rc == 0 && d.hi_rank >= 0 && d.recv_hi) rc = nccl.Recv(d.recv_hi, d.bytes, kChar, d.hi_rank, nccl.comm, s);
+        if (rc == 0 && d.lo_rank >= 0 && d.recv_lo) rc = nccl.Recv(d.recv_lo, d.bytes, kChar, d.lo_rank, nccl.comm, s);
     }
-    XGB_NCCL(nccl.GroupEnd());
+    const int end_rc = nccl.GroupEnd();      // always close the group, also after a failed call
+    if (rc != 0 || end_rc != 0)
+        return fail(std::string("xgb_halo_exchange: ") +
+                    (nccl.GetErrorString ? nccl.GetErrorString(rc != 0 ? rc : end_rc) : "nccl error"));
     return 0;
 }
 

@@ -33,12 +33,17 @@ def slab_range(n0: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class Topology:
-    """Open chain of ranks along axis 0 (overstep 'none' / 'limit')."""
+    """Ranks along axis 0: an open chain (overstep 'none' / 'limit': the global ends have no
+    neighbour, -1), or a ring for overstep 'wrap' (rank 0's lower neighbour is rank P-1, so its lower
+    ghost rows hold the LAST rows of the global grid and the periodic wrap needs no special case)."""
 
-    def __init__(self, rank: int, world: int) -> None:
-        self.rank, self.world = rank, world
-        self.lo_rank = rank - 1 if rank > 0 else -1
-        self.hi_rank = rank + 1 if rank < world - 1 else -1
+    def __init__(self, rank: int, world: int, ring: bool = False) -> None:
+        self.rank, self.world, self.ring = rank, world, bool(ring) and world > 1
+        if self.ring:
+            self.lo_rank, self.hi_rank = (rank - 1) % world, (rank + 1) % world
+        else:
+            self.lo_rank = rank - 1 if rank > 0 else -1
+            self.hi_rank = rank + 1 if rank < world - 1 else -1
 
     @property
     def sharded(self) -> bool:
@@ -51,7 +56,15 @@ _transport = None
 
 def topology() -> Topology:
     """Process topology: from torch.distributed when initialised, else single rank."""
-    global _topology
+    global _topology, _transport
+    from .config import _config
+    ring = _config is not None and _config.overstep == "wrap"
+    if _topology is not None and _topology.ring != (ring and _topology.world > 1):
+        # init() was called again with another overstep mode: same ranks, other neighbours.  The
+        # NCCL communicator is kept (it does not depend on the neighbour relation).
+        _topology = Topology(_topology.rank, _topology.world, ring)
+        if _transport is not None:
+            _transport.topo = _topology
     if _topology is None:
         rank, world = 0, 1
         try:
@@ -60,7 +73,7 @@ def topology() -> Topology:
                 rank, world = dist.get_rank(), dist.get_world_size()
         except ImportError:
             pass
-        _topology = Topology(rank, world)
+        _topology = Topology(rank, world, ring)
     return _topology
 
 

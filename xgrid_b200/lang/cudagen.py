@@ -538,6 +538,8 @@ def _emit_general(g: Group, module: ModuleBuilder, variant: str) -> str:
     def tap(e: ir.Stencil) -> str:
         slot = g.slot(e.variable.name, e.level)
         coords = [f"{adj}(i{a} + ({d}), p.n{a})" for a, d in enumerate(e.space_offset)]
+        # axis 0 of a slab reads its ghost rows where a neighbour exists (open_lo / open_hi; both 0 unsharded)
+        coords[0] = f"{adj}0(i0 + ({e.space_offset[0]}), p.n0, p.open_lo, p.open_hi)"
         lin = coords[0]
         for a in range(1, g.ndim):
             lin = f"({lin}) * p.n{a} + {coords[a]}"

@@ -201,8 +201,11 @@ class Launcher:
             setattr(P, s.field, lv.dev)
         if lead.sharded:
             if self.program.config.overstep != "none":
-                raise Exception("overstep='limit'/'wrap' is not supported on slab-sharded grids yet "
-                                "(the clamp / wrap would need the global extents)")
+                # clamp / wrap along axis 0 happen at the ends of the GLOBAL grid only: where the slab has a
+                # neighbour (chain for "limit", ring for "wrap") the kernel reads its ghost rows instead
+                from .. import dist
+                topo = dist.topology()
+                P.open_lo, P.open_hi = int(topo.lo_rank >= 0), int(topo.hi_rank >= 0)
             self._refresh_halos(g)
         for m in g.masks:
             grid = self.grids[m]
