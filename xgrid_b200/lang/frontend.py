@@ -414,7 +414,14 @@ class Parser:
         for p in parts:
             v = _int_literal(p)
             if v is None:
-                self.error(sub, f"Incompatible subscript '{ast.dump(p)}'")
+                if isinstance(p, (ast.UnaryOp, ast.Constant)):
+                    self.error(sub, f"Incompatible subscript '{ast.dump(p)}'")
+                # parser.py:483-503 only inspects unary-minus and constant nodes; any other expression
+                # (a name, ``1 + 1`` ...) falls through with offset 0.  Same result here, but say so.
+                self.logger.warn(f"File {self.file}, line {getattr(sub, 'lineno', 1) - 1}, in {self.name}",
+                                 f"  subscript '{ast.unparse(p)}' of grid '{var.name}' is not an integer literal; "
+                                 "like the reference, it is taken as offset 0")
+                v = 0
             offsets.append(v)
         if len(offsets) != var.type.dimension:
             self.error(sub, f"Incompatible subscript length '{len(offsets)}' with dimension {var.type.dimension}")
@@ -433,6 +440,12 @@ class Parser:
                 t = _int_literal(node.slice)
                 if t is None:
                     self.error(node.value, "Invalid time dimension subscript")
+                if _ctx(node) == "store":
+                    # the inner subscript of a store target has a *load* context in the Python AST, so the
+                    # reference ends up with a load outside a stencil statement (generator.py:56-65): a store
+                    # cannot name its time level -- it always writes level 0
+                    name = node.value.value.id if isinstance(node.value.value, ast.Name) else "?"
+                    self.error(node, f"Unable to perform load operation to grid '{name}' without stencil context")
                 return self.stencil(node.value, t)
             # default time level: store -> 0, load -> -1 (parser.py:523)
             return self.stencil(node, 0 if _ctx(node) == "store" else -1)
