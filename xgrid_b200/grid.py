@@ -43,6 +43,7 @@ def _flush() -> None:
 SLACK = 64          # elements of linear slack before / after the padded array
 CHUNK = 128         # points per mask flag (XGB_CHUNK in xgb_stencil.cuh)
 MASK_GHOST = 64     # bytes of "outside" (255) mask on both sides of the device mask
+SMALL_MASK = 1 << 20  # masks up to this many points are checked for "all zero" on the host
 ALIGN = 256
 
 
@@ -68,6 +69,8 @@ class _Level:
 
 
 class Grid:
+    _instances = 0
+
     def __init__(self, shape, dtype) -> None:
         self.logger = Logger(self)
         elem = parse_annotation(dtype)
@@ -111,6 +114,8 @@ class Grid:
         self._pair_ok: dict = {}        # (pair id, mask version) -> fused-pair eligibility (lang/jacobi2.py)
         self._mask_hist = None
         self._ghost = 1                 # zero rows on both sides of axis 0
+        Grid._instances += 1
+        self._serial = Grid._instances  # part of every recorded CUDA graph's key: device addresses can repeat
         self._allocs: list[int] = []    # raw device allocations to free
         self._rt = None
 
@@ -277,6 +282,8 @@ class Grid:
             lv.host = np.zeros(self.shape, self.numpy_dtype)
         elif lv.where == "device":
             if lv.host is None:
+                lv.host = self._adopt_stale_mirror(lv)
+            if lv.host is None:
                 lv.host = np.empty(self.shape, self.numpy_dtype)
             rt = self._runtime()
             self._pin(lv)
@@ -285,6 +292,22 @@ class Grid:
         # the caller may write through the returned array: the host owns the level now
         lv.where = "host"
         return lv.host
+
+    def _adopt_stale_mirror(self, lv: _Level):
+        """A level without a host mirror takes over the mirror of a SPARE level (a buffer that left the
+        ring when a several-steps launch wrote into fresh levels; its host copy is stale and no public
+        accessor reaches it any more).  Downloading into memory that is already resident -- and possibly
+        already page-locked -- avoids first-touch page faults on a fresh array (measured: 28 ms -> pageable
+        copy time for a 128 MiB level).  Like the reference's ring, an array handed out by `.now` earlier may
+        therefore be written again later."""
+        for donor in self._spares:
+            if donor.host is not None and donor.where == "device" and donor.host.shape == tuple(self.shape):
+                host, donor.host = donor.host, None
+                if donor.pinned:
+                    lv.pinned, donor.pinned = donor.pinned, 0
+                donor.xfers = 0
+                return host
+        return None
 
     def _to_device(self, lv: _Level) -> None:
         if lv.dev == 0:
@@ -373,21 +396,23 @@ class Grid:
         self._mask_touched = False
         b = self._boundary
         if self._mask_snapshot is not None and np.array_equal(b, self._mask_snapshot):
-            return
+            return                      # touched but unchanged: keep the version (graphs, index lists)
         rt = self._runtime()
         for ptr, _ in self._lists.values():
             if ptr:
                 rt.free(ptr)
         self._lists = {}
-        self._mask_snapshot = b.copy()
+        self._mask_snapshot = None
         self._mask_hist = None
         self._mask_version += 1
         flat = b.reshape(-1)
         nchunk = (self.size + CHUNK - 1) // CHUNK
-        if not flat.any() and not self.sharded:
+        # small grids: look on the host; big ones are classified by the histogram the device pass returns
+        # (a host scan of a 2^24-point int32 mask costs ~8 ms, the device pass reads it anyway)
+        if self.size <= SMALL_MASK and not flat.any() and not self.sharded:
+            self._mask_snapshot = np.zeros(self.shape, np.uint8)
             self._mask_any = False      # all-zero class: kernels get null mask pointers
             return
-        self._mask_any = True
         # device layout: [MASK_GHOST bytes of 255 | mask | zero padding to a whole chunk | MASK_GHOST x 255];
         # 255 = "outside the grid" (never matches a statement); on a sharded 1-D grid the ghost bytes
         # are replaced by the neighbours' edge masks
@@ -402,7 +427,11 @@ class Grid:
                                  nchunk * CHUNK)
         if bad:
             self.logger.dead("boundary mask values must lie in [0, 254] on the B200 backend")
+        # host copy for change detection / index lists / the fused-pair check: one byte per point
+        # (values were just validated), a quarter of the int32 array's traffic
+        self._mask_snapshot = b.astype(np.uint8)
         self._mask_hist = hist
+        self._mask_any = bool(self.sharded or int(hist[0]) != self.size)
         if self.sharded and self.dimension == 1:
             from . import dist
             # trailing ghost sits right after the last real byte on the neighbour's side

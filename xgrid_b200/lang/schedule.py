@@ -591,6 +591,11 @@ class Program:
                 self._bind(args)        # type / arity errors surface at the call site
                 if not self._preloaded:
                     self._preload_batch_kernels()
+                if not grid.sharded and len(grid._spares) < (2 if self.batchable else 1):
+                    # output levels of the several-steps kernels: allocate with the first deferred call, in
+                    # the ghost layout the flush will ask for (a sharded grid decides that at flush time)
+                    grid._ensure_ghost(1 if self.batchable else self.groups[0].tiled2["ghost"])
+                    grid._spare_levels(2 if self.batchable else 1)
                 _PENDING = {"program": self, "args": args, "grid": grid, "key": key, "count": 1}
                 return None
         if _PENDING is not None:
@@ -826,7 +831,10 @@ class Program:
         parts = []
         for name, t in self.ir.signature.arguments:
             if isinstance(t, GridT):
-                parts.append(grids[name]._arrangement() + (grids[name]._mask_version, grids[name].shape))
+                # the grid's serial: a recorded graph also bakes in mask / index-list pointers, and a new
+                # grid can get the very addresses a dead one had (caching pool, or cudaMalloc itself)
+                parts.append(grids[name]._arrangement() + (grids[name]._mask_version, grids[name].shape,
+                                                           grids[name]._serial))
             elif isinstance(t, Pointer):
                 parts.append(_deref(env[name]))
             elif isinstance(t, Structure):

@@ -131,6 +131,9 @@ class Runtime:
         check(self.l.xgb_get_device_info(C.byref(info)))
         self.info = info
         self.sm_count = int(info.sm_count)
+        self._pool: dict = {}            # bytes -> [device pointers] (freed, reusable)
+        self._pool_bytes = 0
+        self._sizes: dict = {}           # live device pointer -> bytes
         if info.cc_major != 10:
             raise Exception(f"xgrid_b200 targets sm_100a (B200); device '{info.name.decode()}' is "
                             f"sm_{info.cc_major}{info.cc_minor}")
@@ -143,13 +146,53 @@ class Runtime:
         return cls._instance
 
     # ---- memory
+    # Caching pool for large device buffers (time levels, masks).  cudaFree synchronises the device and
+    # returns the pages to the driver (measured on B200: ~100 ms per freed 128 MiB level, and the next
+    # cudaMalloc of that size pays again), so freed buffers of >= POOL_MIN bytes are kept by exact size and
+    # handed out again zero-filled, which is what xgb_alloc guarantees.  Re-use is ordered on the compute
+    # stream (the memset is enqueued there); processes that also run a communication stream (sharded grids)
+    # bypass the pool.  The pool is dropped when an allocation fails and at most POOL_CAP bytes are kept.
+    POOL_MIN = 1 << 20
+    POOL_CAP = int(float(os.environ.get("XGB_POOL_GB", "24")) * (1 << 30))
+
     def alloc(self, nbytes: int) -> int:
-        p = c_void_p()
-        check(self.l.xgb_alloc(nbytes, C.byref(p)))
-        return p.value
+        nbytes = int(nbytes)
+        cached = self._pool.get(nbytes)
+        if cached:
+            ptr = cached.pop()
+            self._pool_bytes -= nbytes
+            check(self.l.xgb_memset(c_void_p(ptr), 0, nbytes, 0))
+        else:
+            p = c_void_p()
+            if self.l.xgb_alloc(nbytes, C.byref(p)) != 0:
+                if not self._pool_bytes:
+                    check(1)
+                self.trim_pool()                 # out of memory with buffers cached: release them, retry once
+                check(self.l.xgb_alloc(nbytes, C.byref(p)))
+            ptr = p.value
+        self._sizes[ptr] = nbytes
+        return ptr
 
     def free(self, ptr: int) -> None:
+        nbytes = self._sizes.pop(ptr, 0)
+        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP and self._pooling():
+            self._pool.setdefault(nbytes, []).append(ptr)
+            self._pool_bytes += nbytes
+            return
         self.l.xgb_free(c_void_p(ptr))
+
+    @staticmethod
+    def _pooling() -> bool:
+        from .. import dist
+        return dist._transport is None
+
+    def trim_pool(self) -> None:
+        """Return every cached buffer to the driver."""
+        for cached in self._pool.values():
+            for ptr in cached:
+                self.l.xgb_free(c_void_p(ptr))
+        self._pool.clear()
+        self._pool_bytes = 0
 
     def memset(self, ptr: int, byte: int, nbytes: int, stream: int = 0) -> None:
         check(self.l.xgb_memset(c_void_p(ptr), byte, nbytes, stream))
