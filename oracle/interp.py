@@ -54,6 +54,8 @@ class Interp:
         self.op = operator
         self.d = operator.ir
         self.depth = self.d.depth
+        from xgrid_b200.config import get_config
+        self.overstep = get_config().overstep             # "none" | "limit" | "wrap" (generator.py:172-177)
 
     # ------------------------------------------------------------------ call
     def __call__(self, *args):
@@ -145,6 +147,13 @@ class Interp:
         g = self.grids[e.variable.name]
         assert g.shape == lead.shape, "all grids of one statement must have the same shape"
         level = g._data[e.level]
+        if self.overstep != "none":
+            # per-axis clamped / wrapped coordinates, extents paired correctly
+            idx = []
+            for n, d in zip(g.shape, e.space_offset):
+                i = np.arange(n) + d
+                idx.append(np.clip(i, 0, n - 1) if self.overstep == "limit" else np.mod(i, n))
+            return level[np.ix_(*idx)]
         raw = level.base                                  # the padded 1-D buffer
         off, stride = 0, 1
         for n, d in zip(reversed(g.shape), reversed(e.space_offset)):

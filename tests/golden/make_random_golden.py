@@ -32,25 +32,23 @@ from randprog import gen_inputs, gen_source, guard_array_ends, load_program     
 CASES = [(s, 1, 1 + s % 3, [(37,), (301,), (1000,)][s % 3], False) for s in range(100, 112)]
 CASES += [(s, 2, 1 + s % 3, [(17, 17), (24, 24), (33, 33)][s % 3], False) for s in range(112, 130)]
 CASES += [(s, 1, 1, (500,), True) for s in range(130, 134)]
+# overstep="wrap" / "limit": taps never leave the array, so no guard band is needed
+OVERSTEP_CASES = [(s, 1, 1 + s % 2, [(301,), (1000,)][s % 2], False) for s in range(200, 202)]
+OVERSTEP_CASES += [(s, 2, 1 + s % 3, [(17, 17), (24, 24), (33, 33), (40, 40)][s % 4], False) for s in range(202, 206)]
 CALLS = 3
 A, B = 0.3, 1.7
 
 
-def main():
-    os.chdir(tempfile.mkdtemp(prefix="xgrid_randgold_"))
-    sys.path.insert(0, REF)
-    import xgrid
-    from xgrid.util.logging import Logger, LogLevel
-    Logger.level = LogLevel.warn
-    xgrid.init(precision="double", opt_level=3, cacheroot=".xg", parallel=True)
+def run_cases(xgrid, cases, guard: bool) -> dict:
     out = {}
-    for seed, ndim, ngrids, shape, single in CASES:
+    for seed, ndim, ngrids, shape, single in cases:
         src = gen_source(seed, ndim, ngrids, single_1d=single)
         ref_src = src.replace("import xgrid_b200 as xgrid", "import xgrid")
         assert ref_src != src
-        prog = load_program(ref_src, os.getcwd(), f"refprog_{seed}")
+        prog = load_program(ref_src, os.getcwd(), f"refprog_{seed}_{len(os.listdir(os.getcwd()))}")
         ics, masks = gen_inputs(seed, shape, ngrids)
-        guard_array_ends(masks, shape)      # no statement may read outside the array (undefined in the reference)
+        if guard:
+            guard_array_ends(masks, shape)      # no statement may read outside the array (undefined in the reference)
         grids = []
         for ic, m in zip(ics, masks):
             g = xgrid.Grid(shape, float)
@@ -66,8 +64,22 @@ def main():
             for lvl, arr in enumerate(g._data):
                 out[f"{seed}.g{n}.L{lvl}"] = np.array(arr)
         print("ran", seed, shape, "depth", len(grids[0]._data))
-    np.savez_compressed(os.path.join(HERE, "randprog.npz"), **out)
-    print("wrote randprog.npz", os.path.getsize(os.path.join(HERE, "randprog.npz")), "bytes")
+    return out
+
+
+def main():
+    os.chdir(tempfile.mkdtemp(prefix="xgrid_randgold_"))
+    sys.path.insert(0, REF)
+    import xgrid
+    from xgrid.util.logging import Logger, LogLevel
+    Logger.level = LogLevel.warn
+    for mode, cases, name in (("none", CASES, "randprog"), ("wrap", OVERSTEP_CASES, "randprog_wrap"),
+                              ("limit", OVERSTEP_CASES, "randprog_limit")):
+        xgrid.init(precision="double", opt_level=3, cacheroot=f".xg_{mode}", parallel=True, overstep=mode)
+        out = run_cases(xgrid, cases, guard=(mode == "none"))
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

@@ -81,37 +81,41 @@ def test_fp32_mixed_precision(golden, tmp_path):
         eq(u._data[1], g["u.L1"])
 
 
-def _random_cases():
+def _random_cases(name):
     import os
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "randprog.npz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
     data = np.load(path)
-    seeds = sorted({int(k.split(".")[0]) for k in data.files})
-    return data, seeds
+    return data, sorted({int(k.split(".")[0]) for k in data.files})
 
 
-_RAND, _SEEDS = _random_cases()
+_RAND = {mode: _random_cases(name) for mode, name in
+         (("none", "randprog"), ("wrap", "randprog_wrap"), ("limit", "randprog_limit"))}
 
 
-@pytest.mark.parametrize("seed", _SEEDS)
-def test_random_programs_match_reference(tmp_path, seed):
-    """tests/golden/randprog.npz: the programs of tests/randprog.py run by the UNMODIFIED reference
-    (tests/golden/make_random_golden.py).  The interpreter must reproduce every ring level bit for bit."""
+@pytest.mark.parametrize("mode,seed", [(m, s) for m, (_, seeds) in _RAND.items() for s in seeds])
+def test_random_programs_match_reference(tmp_path, mode, seed):
+    """tests/golden/randprog*.npz: the programs of tests/randprog.py run by the UNMODIFIED reference
+    (tests/golden/make_random_golden.py), with overstep="none" (cells whose taps could leave the array are
+    masked out: undefined in the reference), "wrap" and "limit".  The interpreter must reproduce every ring
+    level bit for bit."""
     from randprog import gen_inputs, gen_source, guard_array_ends, load_program
-    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
-    ndim, ngrids, single, *shape = (int(x) for x in _RAND[f"{seed}.meta"])
+    data = _RAND[mode][0]
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), overstep=mode)
+    ndim, ngrids, single, *shape = (int(x) for x in data[f"{seed}.meta"])
     shape = tuple(shape)
     src = gen_source(seed, ndim, ngrids, single_1d=bool(single))
-    assert src == str(_RAND[f"{seed}.src"]), "tests/randprog.py changed: regenerate tests/golden/randprog.npz"
+    assert src == str(data[f"{seed}.src"]), "tests/randprog.py changed: regenerate tests/golden/randprog*.npz"
     prog = load_program(src, str(tmp_path), f"randprog_{seed}")
     ics, masks = gen_inputs(seed, shape, ngrids)
-    guard_array_ends(masks, shape)
+    if mode == "none":
+        guard_array_ends(masks, shape)
     grids = [host(ic, m) for ic, m in zip(ics, masks)]
     run = Interp(prog)
     for _ in range(3):
         run(*grids, 0.3, 1.7)
     for n, g in enumerate(grids):
-        assert len(g._data) == int(_RAND[f"{seed}.g{n}.depth"])
+        assert len(g._data) == int(data[f"{seed}.g{n}.depth"])
         for lvl, arr in enumerate(g._data):
-            want = _RAND[f"{seed}.g{n}.L{lvl}"]
+            want = data[f"{seed}.g{n}.L{lvl}"]
             bad = np.argwhere(~((arr == want) | (np.isnan(arr) & np.isnan(want))))
             assert len(bad) == 0, f"g{n} level {lvl}: {len(bad)} cells differ, first {bad[:5].tolist()}\n{src}"

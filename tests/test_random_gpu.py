@@ -130,28 +130,34 @@ def test_int_grid_stencil(tmp_path):
 
 # ---- the same generator, but the expected values come from the UNMODIFIED reference itself
 # (tests/golden/randprog.npz, written by tests/golden/make_random_golden.py): CUDA path vs reference,
-# no interpreter in between.  Every third stored program (the whole set is replayed through the
-# interpreter on CPU in tests/test_interp.py).
+# no interpreter in between.  Every third stored program, and every second one of the overstep="wrap" /
+# "limit" sets (all of them are replayed through the interpreter on CPU in tests/test_interp.py).
 def _reference_cases():
     import os
-    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "randprog.npz"))
-    return data, sorted({int(k.split(".")[0]) for k in data.files})[::3]
+    out = []
+    for mode, name, step in (("none", "randprog", 3), ("wrap", "randprog_wrap", 2), ("limit", "randprog_limit", 2)):
+        data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+        for seed in sorted({int(k.split(".")[0]) for k in data.files})[::step]:
+            out.append((mode, seed, data))
+    return out
 
 
-_REFDATA, _REFSEEDS = _reference_cases()
+_REFCASES = _reference_cases()
 
 
-@pytest.mark.parametrize("seed", _REFSEEDS)
-def test_random_program_against_reference_outputs(tmp_path, seed):
+@pytest.mark.parametrize("mode,seed", [(m, s) for m, s, _ in _REFCASES])
+def test_random_program_against_reference_outputs(tmp_path, mode, seed):
     from randprog import guard_array_ends
-    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
-    ndim, ngrids, single, *shape = (int(x) for x in _REFDATA[f"{seed}.meta"])
+    data = next(d for m, s, d in _REFCASES if (m, s) == (mode, seed))
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), overstep=mode)
+    ndim, ngrids, single, *shape = (int(x) for x in data[f"{seed}.meta"])
     shape = tuple(shape)
     src = gen_source(seed, ndim, ngrids, single_1d=bool(single))
-    assert src == str(_REFDATA[f"{seed}.src"]), "tests/randprog.py changed: regenerate tests/golden/randprog.npz"
+    assert src == str(data[f"{seed}.src"]), "tests/randprog.py changed: regenerate tests/golden/randprog*.npz"
     prog = load_program(src, str(tmp_path), f"randprog_ref_{seed}")
     ics, masks = gen_inputs(seed, shape, ngrids)
-    guard_array_ends(masks, shape)
+    if mode == "none":
+        guard_array_ends(masks, shape)      # out-of-array taps are undefined in the reference
     dev = []
     for ic, m in zip(ics, masks):
         g = xgrid.Grid(shape, float)
@@ -162,8 +168,8 @@ def test_random_program_against_reference_outputs(tmp_path, seed):
         prog(*dev, 0.3, 1.7)
     for n, g in enumerate(dev):
         got = g._data
-        assert len(got) == int(_REFDATA[f"{seed}.g{n}.depth"])
+        assert len(got) == int(data[f"{seed}.g{n}.depth"])
         for lvl, x in enumerate(got):
-            want = _REFDATA[f"{seed}.g{n}.L{lvl}"]
+            want = data[f"{seed}.g{n}.L{lvl}"]
             assert np.array_equal(x, want, equal_nan=True), (f"g{n} level {lvl}: "
                                                              f"{int((x != want).sum())} cells differ\n{src}")
