@@ -35,11 +35,14 @@ CASES += [(s, 1, 1, (500,), True) for s in range(130, 134)]
 # overstep="wrap" / "limit": taps never leave the array, so no guard band is needed
 OVERSTEP_CASES = [(s, 1, 1 + s % 2, [(301,), (1000,)][s % 2], False) for s in range(200, 202)]
 OVERSTEP_CASES += [(s, 2, 1 + s % 3, [(17, 17), (24, 24), (33, 33), (40, 40)][s % 4], False) for s in range(202, 206)]
+# precision="float": fp32 grids and scalars, double literals (C's mixed-precision typing)
+FP32_CASES = [(s, 1, 1 + s % 2, [(301,), (1000,)][s % 2], False) for s in range(300, 303)]
+FP32_CASES += [(s, 2, 1 + s % 3, [(17, 17), (24, 24), (33, 33)][s % 3], False) for s in range(303, 309)]
 CALLS = 3
 A, B = 0.3, 1.7
 
 
-def run_cases(xgrid, cases, guard: bool) -> dict:
+def run_cases(xgrid, cases, guard: bool, dtype=np.float64) -> dict:
     out = {}
     for seed, ndim, ngrids, shape, single in cases:
         src = gen_source(seed, ndim, ngrids, single_1d=single)
@@ -52,7 +55,8 @@ def run_cases(xgrid, cases, guard: bool) -> dict:
         grids = []
         for ic, m in zip(ics, masks):
             g = xgrid.Grid(shape, float)
-            g.now[...] = ic
+            assert g.now.dtype == dtype
+            g.now[...] = ic.astype(dtype)
             g.boundary[...] = m
             grids.append(g)
         for _ in range(CALLS):
@@ -73,10 +77,13 @@ def main():
     import xgrid
     from xgrid.util.logging import Logger, LogLevel
     Logger.level = LogLevel.warn
-    for mode, cases, name in (("none", CASES, "randprog"), ("wrap", OVERSTEP_CASES, "randprog_wrap"),
-                              ("limit", OVERSTEP_CASES, "randprog_limit")):
-        xgrid.init(precision="double", opt_level=3, cacheroot=f".xg_{mode}", parallel=True, overstep=mode)
-        out = run_cases(xgrid, cases, guard=(mode == "none"))
+    for mode, cases, name, precision in (("none", CASES, "randprog", "double"),
+                                         ("wrap", OVERSTEP_CASES, "randprog_wrap", "double"),
+                                         ("limit", OVERSTEP_CASES, "randprog_limit", "double"),
+                                         ("none", FP32_CASES, "randprog_f32", "float")):
+        xgrid.init(precision=precision, opt_level=3, cacheroot=f".xg_{name}", parallel=True, overstep=mode)
+        out = run_cases(xgrid, cases, guard=(mode == "none"),
+                        dtype=np.float64 if precision == "double" else np.float32)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path), "bytes")

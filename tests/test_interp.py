@@ -89,7 +89,7 @@ def _random_cases(name):
 
 
 _RAND = {mode: _random_cases(name) for mode, name in
-         (("none", "randprog"), ("wrap", "randprog_wrap"), ("limit", "randprog_limit"))}
+         (("none", "randprog"), ("wrap", "randprog_wrap"), ("limit", "randprog_limit"), ("f32", "randprog_f32"))}
 
 
 @pytest.mark.parametrize("mode,seed", [(m, s) for m, (_, seeds) in _RAND.items() for s in seeds])
@@ -100,16 +100,20 @@ def test_random_programs_match_reference(tmp_path, mode, seed):
     level bit for bit."""
     from randprog import gen_inputs, gen_source, guard_array_ends, load_program
     data = _RAND[mode][0]
-    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), overstep=mode)
+    dtype = np.float32 if mode == "f32" else np.float64
+    if mode == "f32":       # fp32 grids / scalars, double literals (SURVEY.md F6)
+        xgrid.init(precision="float", cacheroot=str(tmp_path / "xg"))
+    else:
+        xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), overstep=mode)
     ndim, ngrids, single, *shape = (int(x) for x in data[f"{seed}.meta"])
     shape = tuple(shape)
     src = gen_source(seed, ndim, ngrids, single_1d=bool(single))
     assert src == str(data[f"{seed}.src"]), "tests/randprog.py changed: regenerate tests/golden/randprog*.npz"
     prog = load_program(src, str(tmp_path), f"randprog_{seed}")
     ics, masks = gen_inputs(seed, shape, ngrids)
-    if mode == "none":
+    if mode in ("none", "f32"):
         guard_array_ends(masks, shape)
-    grids = [host(ic, m) for ic, m in zip(ics, masks)]
+    grids = [host(ic.astype(dtype), m) for ic, m in zip(ics, masks)]
     run = Interp(prog)
     for _ in range(3):
         run(*grids, 0.3, 1.7)
@@ -117,5 +121,6 @@ def test_random_programs_match_reference(tmp_path, mode, seed):
         assert len(g._data) == int(data[f"{seed}.g{n}.depth"])
         for lvl, arr in enumerate(g._data):
             want = data[f"{seed}.g{n}.L{lvl}"]
+            assert arr.dtype == want.dtype == dtype
             bad = np.argwhere(~((arr == want) | (np.isnan(arr) & np.isnan(want))))
             assert len(bad) == 0, f"g{n} level {lvl}: {len(bad)} cells differ, first {bad[:5].tolist()}\n{src}"
