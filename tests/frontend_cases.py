@@ -39,6 +39,20 @@ class IV:
 def helper(a: float, b: float) -> float:
     return a * b + 1.0
 
+
+def _ext_check(args):
+    return args[0]
+
+
+@xgrid.external(typecheck_override=_ext_check)
+def ext_twice(a: float) -> float:
+    ...
+
+
+v1 = xgrid.grid[Vec, 1]
+pf = xgrid.ptr[float]
+pi = xgrid.ptr[int]
+
 """
 
 CASES = {
@@ -440,6 +454,92 @@ def k(u: f1) -> None:
 def k(u: f1, t: int) -> None:
     u[0] = u[0][t]
 """,
+    "struct_grid_load_fields": """
+@xgrid.kernel()
+def k(g: v1, u: f1) -> None:
+    u[0] = g[0].x + g[1].y * 2.0
+""",
+    "struct_grid_store_whole_element": """
+@xgrid.kernel()
+def k(g: v1, u: f1) -> None:
+    g[0] = Vec(u[0], u[-1] * 2.0)
+""",
+    "struct_grid_store_field_rejected": """
+@xgrid.kernel()
+def k(g: v1) -> None:
+    g[0].x = 1.0
+""",
+    "pointer_read_and_write": """
+@xgrid.kernel()
+def k(p: pf, n: pi) -> float:
+    p = p * 2.0 + 1.0
+    n = n + 1
+    return p
+""",
+    "pointer_type_mismatch_rejected": """
+@xgrid.kernel()
+def k(p: pf) -> None:
+    p = 1
+""",
+    "external_call_with_typecheck_override": """
+@xgrid.kernel()
+def k(a: float) -> float:
+    return ext_twice(a) + 1.0
+""",
+    "inline_c_block": """
+@xgrid.kernel()
+def k(u: f1, a: float) -> None:
+    u[0] = u[0] * a
+    with xgrid.c():
+        "/* inline text */"
+""",
+    "inline_c_non_string_rejected": """
+@xgrid.kernel()
+def k(a: int) -> int:
+    with xgrid.c():
+        a = a + 1
+    return a
+""",
+    "import_as_include": """
+@xgrid.kernel()
+def k(a: int) -> int:
+    import stdio
+    import sys.types
+    return a
+""",
+    "tick_call_inside_kernel": """
+@xgrid.kernel()
+def k(u: f1) -> None:
+    u[0] = u[0] * 0.5
+    xgrid.tick(u)
+""",
+    "shape_of_non_grid_rejected": """
+@xgrid.kernel()
+def k(a: int) -> int:
+    return xgrid.shape(a, 0)
+""",
+    "dimension_in_scalar_kernel": """
+@xgrid.kernel()
+def k(u: f2) -> int:
+    return xgrid.dimension(u) * 10 + 1
+""",
+    "with_unknown_context_rejected": """
+@xgrid.kernel()
+def k(a: int) -> int:
+    with open("x"):
+        a = a + 1
+    return a
+""",
+    "nested_function_call_in_stencil": """
+@xgrid.kernel()
+def k(u: f1, a: float) -> None:
+    u[0] = helper(u[0], a) + helper(a, u[1])
+""",
+    "method_call_in_stencil": """
+@xgrid.kernel()
+def k(u: f1, p: Vec) -> None:
+    u[0] = p.dot(Vec(u[0], u[-1]))
+""",
     "grid_as_return_type_rejected": """
 @xgrid.kernel()
 def k(u: f1) -> f1:
@@ -449,6 +549,9 @@ def k(u: f1) -> f1:
 
 # Cases where this backend deliberately differs from the reference's front end.
 DEVIATIONS = {
+    "tick_call_inside_kernel": "the reference parses an in-kernel xgrid.tick(u) but the C it generates "
+                               "(`extern void tick(None grid);`) fails to compile at the first call (SURVEY.md F9); "
+                               "this backend rejects it at parse time with a message that says so",
     "stencil_two_argument_boundary": "the stale two-argument form of test.py:217 is accepted as an alias so that "
                                      "test.py runs unmodified (SURVEY.md §8f rank 2); the reference rejects it (F3)",
 }

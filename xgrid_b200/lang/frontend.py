@@ -508,6 +508,12 @@ class Parser:
                 self.error(node, f"Invalid call to object '{func}', it is not an operator")
         if fname is None:
             fname = func.name
+        if isinstance(func, Operator) and func.mode == "external" and func.name == "tick" \
+                and func.func.__module__.split(".")[0] == __name__.split(".")[0]:
+            # the reference parses this call but its generated C (`extern void tick(None grid);`)
+            # never compiles, so no working program contains it.  Say so instead of emitting dead code.
+            self.error(node, "xgrid.tick inside a kernel is a dead feature of the reference (its generated C does "
+                             "not compile); every Grid argument is ticked once by the kernel call itself")
 
         want = func.signature.arguments
         if len(want) != len(args):
