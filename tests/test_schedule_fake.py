@@ -1,0 +1,131 @@
+"""Host side of a kernel call on a recording fake runtime (tests/fake_runtime.py): what is launched, in
+which order, with which buffers -- deferral and flushing, the multi-step launch plan, ring rotation by
+pointer, scratch swaps, CUDA-graph recording / replay keys and the device-memory pool.  CPU only; the
+numbers these launches produce are checked by the GPU suite."""
+import numpy as np
+import pytest
+
+import xgrid_b200 as xgrid
+from xgrid_b200 import workloads as W
+
+import fake_runtime
+
+
+@pytest.fixture()
+def rt(monkeypatch, tmp_path):
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+    return fake_runtime.install(monkeypatch)
+
+
+def test_1d_run_is_deferred_and_split_into_multistep_launches(rt):
+    k = W.make_kernels()["convection_1d"]
+    n = 1 << 16
+    u = xgrid.Grid((n,), float)
+    u.now[...] = 1.0
+    u.boundary[0] = 1
+    for _ in range(150):
+        k(u, 1.0, 0.5, 1.0)
+    assert rt.launches == []                                  # nothing ran yet: 150 identical calls are queued
+    xgrid.flush()
+    names = rt.names()
+    assert names == (["xg_convection_1d_g0_multistep_v1"] * 2 + ["xg_convection_1d_g0_multistep_tail_v1"]
+                     + ["xg_convection_1d_g0_dense_v4"] * 2), names
+    full, tail = rt.launches[0][3], rt.launches[2][3]
+    assert tail["opt0"] == 20 and full["n0"] == n
+    # every launch reads the two ring levels and writes two other buffers, which then become the ring
+    assert len({full["aux0"], full["aux1"], full["aux2"], full["aux3"]}) == 4
+    second = rt.launches[1][3]
+    assert (second["aux0"], second["aux1"]) == (full["aux2"], full["aux3"])
+    assert (second["aux2"], second["aux3"]) == (full["aux0"], full["aux1"])
+    assert len(u._ring) == 2 and len(u._spares) == 2
+
+
+def test_changing_a_scalar_or_reading_now_flushes(rt):
+    k = W.make_kernels()["convection_1d"]
+    u = xgrid.Grid((1 << 15,), float)
+    for _ in range(10):
+        k(u, 1.0, 0.5, 1.0)
+    k(u, 1.0, 0.25, 1.0)                                      # other arguments: the queued run executes first
+    assert rt.names() == ["xg_convection_1d_g0_multistep_tail_v1", "xg_convection_1d_g0_dense_v4",
+                          "xg_convection_1d_g0_dense_v4"]
+    before = len(rt.launches)
+    _ = u.now                                                 # host read: flush the one pending call, then D2H
+    assert len(rt.launches) == before + 1 and rt.copies[-1][0] == "d2h"
+
+
+def test_ring_rotates_by_pointer_and_graph_replays_after_recording(rt):
+    k = W.make_kernels()["elementwise_mul"]
+    n = 10000
+    r, a, b = (xgrid.Grid((n,), float) for _ in range(3))
+    a.now[...] = 2.0
+    b.now[...] = 3.0
+    seen = []
+    for call in range(6):
+        k(r, a, b)
+        p = rt.launches[-1][3]
+        seen.append((p["s0"], p["s1"], p["s2"]))
+    # depth 2: every grid's two buffers alternate (store level 0 of r, load level 1 of a and b)
+    assert seen[0] == seen[2] == seen[4] and seen[1] == seen[3] == seen[5] and seen[0] != seen[1]
+    assert all(len(set(s)) == 3 for s in seen)
+    # arrangement A is seen at call 0, recorded at call 2, replayed at call 4 (B: 1, 3, 5)
+    assert len(rt.graphs) == 2 and len(rt.launches) == 6
+    uploads = [c for c in rt.copies if c[0] == "h2d"]
+    assert len(uploads) == 3                                   # each grid's first level once; second levels start as device zeros
+
+
+def test_new_grid_never_replays_a_dead_grids_graph(rt):
+    """Device addresses repeat (pool / cudaMalloc): the grid serial in the graph key keeps recorded
+    launches -- which also bake in mask and index-list pointers -- from being replayed for another grid."""
+    k = W.make_kernels()["diffusion_1d"]
+    n = 4096                                                  # below the deferral threshold: direct calls
+
+    def run():
+        u = xgrid.Grid((n,), float)
+        u.boundary[0] = u.boundary[-1] = 1
+        for _ in range(4):
+            k(u, 0.01, 0.1, 1.0)
+        return u._arrangement(), u._mask_dev
+
+    first, mask1 = run()
+    graphs_after_first = len(rt.graphs)
+    second, mask2 = run()
+    assert len(rt.graphs) == 2 * graphs_after_first           # recorded again for the new grid
+
+
+def test_cavity_call_structure_and_graph(rt):
+    k = W.make_kernels()["cavity_kernel"]
+    nn = 64                                                   # small: the fused Jacobi pairs need >= MIN_COLS columns
+    mb, mp, mu, mv = W.cavity_masks(nn, nn)
+    gs = [xgrid.Grid((nn, nn), float) for _ in range(4)]
+    for g, m in zip(gs, (mb, mp, mu, mv)):
+        g.boundary[...] = m
+    cfg = W.Config(1.0, 0.1, 1e-4, 2.0 / (nn - 1), 2.0 / (nn - 1))
+    k(*gs, cfg)
+    first = rt.names()
+    sparse = [x for x in first if x.endswith("_sparse_v1")]
+    # b, p-first, 4 BCs, 50 x (Jacobi + 4 BCs), fused tail (u, v, 3 Dirichlet BCs in ONE launch)
+    assert len(first) == 1 + 1 + 4 + 50 * 5 + 1 and len(sparse) == 4 + 50 * 4, (len(first), len(sparse))
+    n1 = len(rt.launches)
+    k(*gs, cfg)
+    k(*gs, cfg)
+    k(*gs, cfg)
+    assert (len(rt.launches) - n1) == 3 * len(first)          # same work per call, direct, recorded or replayed
+    assert 1 <= len(rt.graphs) <= 2
+
+
+def test_grid_buffers_return_to_the_pool_and_are_reused(rt):
+    k = W.make_kernels()["diffusion_2d"]
+    shape = (512, 1024)                                       # 4 MiB levels: pooled
+
+    def run():
+        u = xgrid.Grid(shape, float)
+        u.boundary[0, :] = 1
+        k(u, 0.2)
+        xgrid.flush()
+        return {lv.raw for lv in u._ring}
+
+    first = run()                                             # the grid dies here: its buffers go to the pool
+    allocs = len(rt.real_alloc_sizes)
+    second = run()
+    assert second == first                                    # the very same level buffers again
+    assert all(b < rt.POOL_MIN for b in rt.real_alloc_sizes[allocs:])      # only small buffers (mask, flags) are new
