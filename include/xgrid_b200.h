@@ -64,6 +64,13 @@ int xgb_host_free(void *hptr);
 int xgb_host_register(void *hptr, size_t bytes); /* pin an existing NumPy mirror */
 int xgb_host_unregister(void *hptr);
 int xgb_mem_info(uint64_t *free_bytes, uint64_t *total_bytes);
+/* Copies between PAGEABLE host memory and the device through page-locked staging chunks filled /
+ * drained by several host threads (replaces: nothing -- the reference's arrays never leave the host;
+ * this is the upload of Grid.now written by the user and the download behind Grid.now).
+ * xgb_h2d_staged returns once the source has been read (the transfer is ordered on `stream` like
+ * xgb_h2d from a pinned buffer); xgb_d2h_staged returns when dst_host is complete. */
+int xgb_h2d_staged(void *dst_dev, const void *src_host, size_t bytes, xgb_handle stream);
+int xgb_d2h_staged(void *dst_host, const void *src_dev, size_t bytes, xgb_handle stream);
 
 /* ---- streams / events --------------------------------------------------- */
 /* stream 0 is the backend's default compute stream (created by xgb_init). */

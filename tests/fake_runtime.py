@@ -70,6 +70,8 @@ class FakeRuntime(shim.Runtime):
     def d2h(self, dst, src, nbytes, stream=0):
         self.copies.append(("d2h", src, nbytes))
 
+    STAGED = False
+
     def d2d(self, dst, src, nbytes, stream=0):
         self.copies.append(("d2d", dst, nbytes))
 

@@ -286,8 +286,12 @@ class Grid:
             if lv.host is None:
                 lv.host = np.empty(self.shape, self.numpy_dtype)
             rt = self._runtime()
-            self._pin(lv)
-            rt.d2h(lv.host.ctypes.data, lv.dev, self.size * self.itemsize)
+            nbytes = self.size * self.itemsize
+            if rt.STAGED and nbytes >= rt.STAGED_MIN and not lv.pinned:
+                rt.d2h_staged(lv.host.ctypes.data, lv.dev, nbytes)      # pageable mirror, several host threads
+            else:
+                self._pin(lv)
+                rt.d2h(lv.host.ctypes.data, lv.dev, nbytes)
             rt.sync()
         # the caller may write through the returned array: the host owns the level now
         lv.where = "host"
@@ -318,10 +322,14 @@ class Grid:
         if lv.where == "host":
             host = np.ascontiguousarray(lv.host)
             lv.host = host
-            self._pin(lv)
-            self._runtime().h2d(lv.dev, host.ctypes.data, self.size * self.itemsize)
-            if lv.pinned:
-                self._runtime().sync()      # the caller may modify the mirror right after
+            rt, nbytes = self._runtime(), self.size * self.itemsize
+            if rt.STAGED and nbytes >= rt.STAGED_MIN and not lv.pinned:
+                rt.h2d_staged(lv.dev, host.ctypes.data, nbytes)         # returns once the mirror has been read
+            else:
+                self._pin(lv)
+                rt.h2d(lv.dev, host.ctypes.data, nbytes)
+                if lv.pinned:
+                    rt.sync()               # the caller may modify the mirror right after
         elif lv.where == "zero":
             self._runtime().memset(lv.dev, 0, self.size * self.itemsize)
         lv.where = "device"

@@ -47,6 +47,8 @@ SIGNATURES = {
     "xgb_h2d": [c_void_p, c_void_p, c_size_t, Handle],
     "xgb_d2h": [c_void_p, c_void_p, c_size_t, Handle],
     "xgb_d2d": [c_void_p, c_void_p, c_size_t, Handle],
+    "xgb_h2d_staged": [c_void_p, c_void_p, c_size_t, Handle],
+    "xgb_d2h_staged": [c_void_p, c_void_p, c_size_t, Handle],
     "xgb_host_alloc": [c_size_t, POINTER(c_void_p)],
     "xgb_host_free": [c_void_p],
     "xgb_host_register": [c_void_p, c_size_t],
@@ -202,6 +204,16 @@ class Runtime:
 
     def d2h(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
         check(self.l.xgb_d2h(c_void_p(dst), c_void_p(src), nbytes, stream))
+
+    # pageable memory through the runtime's multi-threaded staging path (opt-in: XGB_STAGED_COPY=1)
+    STAGED = os.environ.get("XGB_STAGED_COPY", "0") == "1"
+    STAGED_MIN = 8 << 20
+
+    def h2d_staged(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
+        check(self.l.xgb_h2d_staged(c_void_p(dst), c_void_p(src), nbytes, stream))
+
+    def d2h_staged(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
+        check(self.l.xgb_d2h_staged(c_void_p(dst), c_void_p(src), nbytes, stream))
 
     def d2d(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
         check(self.l.xgb_d2d(c_void_p(dst), c_void_p(src), nbytes, stream))
