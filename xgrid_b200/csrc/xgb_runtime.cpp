@@ -184,7 +184,8 @@ struct Nccl {
 // staging buffer (measured on the B200 box: ~11 GB/s up, ~5 GB/s down into a fresh array, against
 // ~33 GB/s for page-locked mirrors).  Here kStageLanes host threads each own two page-locked chunks
 // and a stream: a lane copies its chunks pageable -> pinned (or back) while the copy engine moves the
-// lane's other chunk.  Opt-in from Python (XGB_STAGED_COPY=1) until measured.
+// lane's other chunk.  Correct on hardware (tests/test_staged_copy_gpu.py); opt-in from Python
+// (XGB_STAGED_COPY=1) until it has been timed against the driver's pageable path.
 namespace {
 constexpr int kStageLanes = 4;
 constexpr size_t kStageChunk = size_t(4) << 20;
