@@ -14,6 +14,9 @@ cat $O/${P}_bench_default.json >> $O/${P}_bench_all.jsonl
 for w in conv1d_nl diff1d conv2d diff2d heat3d cavity ewmul; do
   timeout 300 python bench.py --workload $w --cpu-budget 4 >> $O/${P}_bench_all.jsonl 2> $O/${P}_err_$w.log
 done
+# host-path phases of the default job, with the driver's pageable copies and with the staged path
+timeout 100 python scripts/e2e_phases.py conv1d 10000 > $O/${P}_e2e_phases.log 2>&1
+XGB_STAGED_COPY=1 timeout 100 python scripts/e2e_phases.py conv1d 10000 > $O/${P}_e2e_phases_staged.log 2>&1
 # launch lists (per-launch device time under ncu: cold cache, serialised -- compare shares)
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${P}_bench_launches.csv \
     python bench.py --steps 2000 --warmup 200 --no-cpu --no-e2e > /dev/null 2>&1
