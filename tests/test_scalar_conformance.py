@@ -2,7 +2,7 @@
 (tests/randscalar.py) were compiled with gcc and called by the reference
 (tests/golden/make_scalar_golden.py -> randscalar.json); the host evaluator of this backend
 (`lang/schedule.py::HostEval`, which also computes the scalar prologue of every grid kernel) must return
-the same int / the same double bit for bit."""
+the same int / the same double (or, with precision="float", the same float) bit for bit."""
 import importlib.util
 import json
 import os
@@ -13,14 +13,16 @@ import xgrid_b200 as xgrid
 from randscalar import gen_source
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-with open(os.path.join(HERE, "golden", "randscalar.json")) as f:
-    GOLD = json.load(f)
+GOLD = {}
+for _precision, _name in (("double", "randscalar"), ("float", "randscalar_f32")):
+    with open(os.path.join(HERE, "golden", _name + ".json")) as f:
+        GOLD[_precision] = json.load(f)
 
 
-@pytest.mark.parametrize("seed", sorted(GOLD, key=int))
-def test_scalar_kernel_matches_reference(tmp_path, seed):
-    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
-    want = GOLD[seed]
+@pytest.mark.parametrize("precision,seed", [(p, s) for p in GOLD for s in sorted(GOLD[p], key=int)])
+def test_scalar_kernel_matches_reference(tmp_path, precision, seed):
+    xgrid.init(precision=precision, cacheroot=str(tmp_path / "xg"))
+    want = GOLD[precision][seed]
     src, args = gen_source(int(seed))
     assert src == want["src"] and list(args) == want["args"], \
         "tests/randscalar.py changed: regenerate tests/golden/randscalar.json"
