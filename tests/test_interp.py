@@ -124,3 +124,38 @@ def test_random_programs_match_reference(tmp_path, mode, seed):
             assert arr.dtype == want.dtype == dtype
             bad = np.argwhere(~((arr == want) | (np.isnan(arr) & np.isnan(want))))
             assert len(bad) == 0, f"g{n} level {lvl}: {len(bad)} cells differ, first {bad[:5].tolist()}\n{src}"
+
+
+# ---- ring protocol: resize / truncate / rotate-per-argument / tick=False, after every call
+def _ring_scenarios():
+    import ring_cases as RC
+    return sorted(RC.SCENARIOS)
+
+
+@pytest.mark.parametrize("scenario", _ring_scenarios())
+def test_ring_protocol_matches_reference(tmp_path, scenario):
+    """tests/golden/ring_protocol.npz (tests/golden/make_ring_golden.py): the unmodified reference's ring after
+    every call of the scenarios in tests/ring_cases.py; HostGrid + the interpreter must agree bit for bit."""
+    import os
+    import ring_cases as RC
+    import importlib.util
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ring_protocol.npz"))
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+    path = tmp_path / "ring_kernels.py"
+    path.write_text(RC.SOURCE.replace("IMPORT_LINE", "import xgrid_b200 as xgrid"))
+    spec = importlib.util.spec_from_file_location("ring_kernels", str(path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    grids = {}
+    for which in "gh":
+        ic, mask = RC.initial(np, which)
+        grids[which] = host(ic, mask)
+    runners = {}
+    for step, (kernel, spec_) in enumerate(RC.SCENARIOS[scenario]):
+        run = runners.setdefault(kernel, Interp(getattr(mod, kernel)))
+        run(*RC.arguments(spec_, grids))
+        for which, g in grids.items():
+            assert len(g._data) == int(gold[f"{scenario}.{step}.{which}.depth"]), (step, kernel, which)
+            for lvl, arr in enumerate(g._data):
+                want = gold[f"{scenario}.{step}.{which}.L{lvl}"]
+                assert np.array_equal(arr, want, equal_nan=True), (scenario, step, kernel, which, lvl)
