@@ -83,3 +83,15 @@ def test_pool_is_released_when_an_allocation_fails(monkeypatch):
         raise AssertionError("allocation beyond the device capacity must fail loudly")
     rt.trim_pool()
     assert rt.l.used == 70 << 20
+
+
+def test_empty_cache_is_public(monkeypatch):
+    import xgrid_b200 as xgrid
+    monkeypatch.setattr(shim, "last_error", lambda: "fake")
+    rt = make()
+    monkeypatch.setattr(shim.Runtime, "_instance", rt)
+    a = rt.alloc(8 << 20)
+    rt.free(a)
+    assert rt._pool_bytes
+    xgrid.empty_cache()
+    assert rt._pool_bytes == 0 and rt.l.frees == 1

@@ -81,5 +81,13 @@ def synchronize() -> None:
     Runtime.get().sync()
 
 
+def empty_cache() -> None:
+    """Return the device buffers cached by the runtime's pool to the driver (B200 extension; the pool keeps
+    freed time levels for re-use because cudaFree / cudaMalloc of large buffers cost ~100 ms each)."""
+    from .runtime.shim import Runtime
+    if Runtime._instance is not None:
+        Runtime._instance.trim_pool()
+
+
 __all__ = ["kernel", "function", "init", "ptr", "grid", "boundary", "c", "external", "Grid",
-           "shape", "dimension", "tick", "synchronize", "flush"]
+           "shape", "dimension", "tick", "synchronize", "flush", "empty_cache"]
