@@ -55,7 +55,7 @@ class FakeRuntime(shim.Runtime):
     def free(self, ptr: int) -> None:
         nbytes = self._sizes.pop(ptr, 0)
         self.live.pop(ptr, None)
-        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP:
+        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP and self._pooling():
             self._pool.setdefault(nbytes, []).append(ptr)
             self._pool_bytes += nbytes
         else:
@@ -172,3 +172,35 @@ def install(monkeypatch) -> FakeRuntime:
     monkeypatch.setattr(schedule, "_PENDING", None)
     monkeypatch.setattr(launch, "STATS", {})
     return rt
+
+
+class FakeTransport:
+    """Records halo exchanges instead of running NCCL (xgrid_b200/dist.py::NcclTransport's interface)."""
+
+    def __init__(self, topo, rt: FakeRuntime) -> None:
+        self.topo, self.rt, self.log = topo, rt, []
+
+    def exchange(self, items, stream=0):
+        for grid, lv, h in items:
+            self.log.append(("exchange", lv.dev, h, len(self.rt.launches)))
+            lv.halo_ok = True
+
+    def exchange_async(self, items):
+        for grid, lv, h in items:
+            self.log.append(("exchange_async", lv.dev, h, len(self.rt.launches)))
+            lv.halo_ok = True
+            lv.halo_event = self.rt.event_create()
+
+    def exchange_bytes(self, data_ptr, data_bytes, halo_bytes, stream=0):
+        self.log.append(("exchange_bytes", data_ptr, halo_bytes, len(self.rt.launches)))
+
+
+def install_sharded(monkeypatch, rank: int, world: int, ring: bool = False):
+    """Fake runtime + a fixed slab topology + a recording transport (no torch.distributed needed)."""
+    from xgrid_b200 import dist
+    rt = install(monkeypatch)
+    topo = dist.Topology(rank, world, ring)
+    transport = FakeTransport(topo, rt)
+    monkeypatch.setattr(dist, "_topology", topo)
+    monkeypatch.setattr(dist, "_transport", transport)
+    return rt, transport

@@ -129,3 +129,46 @@ def test_grid_buffers_return_to_the_pool_and_are_reused(rt):
     second = run()
     assert second == first                                    # the very same level buffers again
     assert all(b < rt.POOL_MIN for b in rt.real_alloc_sizes[allocs:])      # only small buffers (mask, flags) are new
+
+
+# ---- slab-sharded grids: halo planning and edge-first overlap (host logic of SURVEY.md §8e)
+def test_sharded_3d_sweep_runs_edges_first_and_exchanges_only_stale_levels(monkeypatch, tmp_path):
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    k = W.make_kernels()["heat_3d"]
+    u = xgrid.Grid((4 * 64, 64, 256), float)                  # global shape: this rank owns 64 planes
+    assert u.sharded and u.shape == (64, 64, 256) and u.row_range == (64, 128)
+    u.now[...] = 1.0
+    k(u, 0.1)
+    # first call: the uploaded level is stale -> one blocking exchange BEFORE any launch; then the two edge
+    # bands, the asynchronous exchange of the freshly written level, and the interior band
+    assert tr.log[0][0] == "exchange" and tr.log[0][3] == 0
+    names = rt.names()
+    assert len(names) == 3 and len(set(names)) == 1 and names[0].endswith("_tiled_v2"), names
+    bands = [(r[3]["r_lo"], r[3]["r_hi"]) for r in rt.launches]
+    assert bands == [(0, 1), (63, 64), (1, 63)]
+    assert tr.log[1][0] == "exchange_async" and tr.log[1][3] == 2       # issued after the two edge launches
+    written = rt.launches[0][3]["s0"]
+    assert tr.log[1][1] == written
+    # second call reads the level written by the first: its halo is already in flight -> no new blocking exchange
+    before = len(tr.log)
+    k(u, 0.1)
+    kinds = [e[0] for e in tr.log[before:]]
+    assert kinds == ["exchange_async"], kinds
+    assert rt.launches[3][3]["s1"] == written                 # ring rotated by pointer: last output is now the input
+    # the pool is bypassed while a transport exists (buffers may be in use on the communication stream)
+    del u
+    assert rt._pool_bytes == 0
+
+
+def test_sharded_overstep_sets_open_flags_from_the_topology(monkeypatch, tmp_path):
+    for mode, rank, ring, want in (("wrap", 0, True, (1, 1)), ("limit", 0, False, (0, 1)), ("limit", 3, False, (1, 0))):
+        xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True, overstep=mode)
+        rt, tr = fake_runtime.install_sharded(monkeypatch, rank=rank, world=4, ring=ring)
+        k = W.make_kernels()["diffusion_2d_open"]
+        u = xgrid.Grid((64, 48), float)
+        u.now[...] = 1.0
+        k(u, 0.2)
+        p = rt.launches[-1][3]
+        assert (p["open_lo"], p["open_hi"]) == want, (mode, rank)
+        assert tr.log and tr.log[0][0] == "exchange"          # ghost rows are refreshed before the first sweep
