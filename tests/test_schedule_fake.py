@@ -172,3 +172,68 @@ def test_sharded_overstep_sets_open_flags_from_the_topology(monkeypatch, tmp_pat
         p = rt.launches[-1][3]
         assert (p["open_lo"], p["open_hi"]) == want, (mode, rank)
         assert tr.log and tr.log[0][0] == "exchange"          # ghost rows are refreshed before the first sweep
+
+
+def test_touching_the_mask_without_changing_it_keeps_recorded_graphs(rt):
+    k = W.make_kernels()["diffusion_1d"]
+    u = xgrid.Grid((4096,), float)
+    u.boundary[0] = u.boundary[-1] = 1
+    for _ in range(6):
+        k(u, 0.01, 0.1, 1.0)
+    graphs, version = len(rt.graphs), u._mask_version
+    _ = u.boundary                                            # touched (the property cannot know about writes) ...
+    for _ in range(4):
+        k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == version and len(rt.graphs) == graphs      # ... but unchanged: same version, same graphs
+    u.boundary[7] = 1                                         # a real change: new version, graphs are re-recorded
+    for _ in range(4):
+        k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == version + 1 and len(rt.graphs) > graphs
+
+
+def test_2d_run_executes_two_steps_per_pass_and_stores_the_middle_level_last(rt):
+    k = W.make_kernels()["diffusion_2d"]
+    u = xgrid.Grid((256, 2048), float)
+    u.now[...] = 1.0
+    u.boundary[0, :] = u.boundary[-1, :] = u.boundary[:, 0] = u.boundary[:, -1] = 1
+    for _ in range(7):
+        k(u, 0.2)
+    assert rt.launches == []
+    xgrid.flush()
+    names = rt.names()
+    assert names[:3] == ["xg_diffusion_2d_g0_tiled2_v2"] * 3 and len(names) == 4      # 3 passes of 2 steps + 1 single step
+    assert [r[3]["opt0"] for r in rt.launches[:3]] == [0, 0, 1]                      # only the last pass stores u^{n+1}
+    p0, p1 = rt.launches[0][3], rt.launches[1][3]
+    assert p1["aux0"] == p0["aux1"] and p1["aux1"] == p0["aux0"]                     # u^{n+2} overwrites the dead level
+    # a cell whose mask value has no statement would keep a value from two steps back: no two-step passes then
+    v = xgrid.Grid((256, 2048), float)
+    v.boundary[5, 5] = 7
+    for _ in range(4):
+        k(v, 0.2)
+    n = len(rt.launches)
+    xgrid.flush()
+    assert all(not x.endswith("tiled2_v2") for x in rt.names(n)) and len(rt.launches) - n == 4
+
+
+def test_ghost_relayout_drops_and_rebuilds_device_buffers(rt):
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def near(u: f2) -> None:
+        u[0, 0] = 0.5 * (u[1, 0] + u[-1, 0])
+
+    @xgrid.kernel()
+    def far(u: f2) -> None:
+        u[0, 0] = 0.5 * (u[3, 0] + u[-3, 0])
+
+    u = xgrid.Grid((64, 96), float)
+    u.now[...] = 1.0
+    near(u)
+    assert u._ghost == 1
+    first = {lv.raw for lv in u._ring}
+    far(u)                                                    # needs 3 ghost rows: levels are re-laid-out
+    assert u._ghost == 3 and first.isdisjoint({lv.raw for lv in u._ring})
+    downloads = [c for c in rt.copies if c[0] == "d2h"]
+    assert len(downloads) == 2                                # both device levels came back to the host first
+    near(u)                                                   # a smaller halo keeps the larger layout
+    assert u._ghost == 3
