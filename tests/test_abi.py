@@ -58,3 +58,26 @@ def test_generated_kernels_use_bulk_copy_engine(tmp_path):
     cubin.write_bytes(img)
     sass = subprocess.run(["cuobjdump", "-sass", str(cubin)], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_no_generated_workload_kernel_spills(tmp_path):
+    """Every variant of every workload kernel fits its registers: no local-memory spills in the sm_100a cubins
+    (the small stacks belong to the out-of-line slow path of the exact division)."""
+    import subprocess
+    import xgrid_b200 as xgrid
+    from xgrid_b200 import workloads as W
+    from xgrid_b200.lang.schedule import Program
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+    seen = 0
+    for name, op in W.make_kernels().items():
+        prog = Program(op)
+        if not prog.source:
+            continue
+        cubin = tmp_path / f"{name}.cubin"
+        cubin.write_bytes(prog.image())
+        out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(cubin)], capture_output=True, text=True).stdout
+        for m in re.finditer(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out):
+            regs, stack, _, local = map(int, m.groups())
+            seen += 1
+            assert local == 0 and regs <= 255 and stack <= 64, (name, m.group(0))
+    assert seen >= 100
