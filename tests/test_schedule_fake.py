@@ -237,3 +237,39 @@ def test_ghost_relayout_drops_and_rebuilds_device_buffers(rt):
     assert len(downloads) == 2                                # both device levels came back to the host first
     near(u)                                                   # a smaller halo keeps the larger layout
     assert u._ghost == 3
+
+
+# ---- CUDA-graph replay must be indistinguishable from issuing the launches directly
+@pytest.mark.parametrize("seed,ndim,ngrids,shape", [
+    (8, 2, 3, (40, 1030)), (11, 2, 3, (64, 1024)), (13, 2, 2, (17, 33)), (21, 3, 2, (18, 9, 130)),
+    (24, 3, 1, (20, 16, 256)), (3, 1, 2, (4100,)), (5, 1, 2, (37,)),
+])
+def test_graph_replay_issues_exactly_the_direct_launch_sequence(monkeypatch, tmp_path, seed, ndim, ngrids, shape):
+    """Random multi-grid programs (tests/randprog.py: time levels 0..2, implicit statements, loops, sparse
+    boundary statements, host control flow), 26 calls each, once with CUDA graphs (record on the second
+    sighting of a buffer arrangement, replay afterwards) and once without: kernel names, geometry and every
+    parameter -- i.e. every buffer pointer in every role -- must be identical launch by launch."""
+    from randprog import gen_inputs, gen_source, load_program
+    src = gen_source(seed, ndim, ngrids)
+    traces = []
+    for graphs in (True, False):
+        xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), graphs=graphs)
+        rt = fake_runtime.install(monkeypatch)
+        prog = load_program(src, str(tmp_path), f"randprog_{seed}_{int(graphs)}")
+        ics, masks = gen_inputs(seed, shape, ngrids)
+        grids = []
+        for ic, m in zip(ics, masks):
+            g = xgrid.Grid(shape, float)
+            g.now[...] = ic
+            g.boundary[...] = m
+            grids.append(g)
+        for _ in range(26):
+            prog(*grids, 0.3, 1.7)
+        xgrid.flush()
+        traces.append((list(rt.launches), len(rt.graphs)))
+        del grids
+    (with_graphs, n_graphs), (direct, none) = traces
+    assert none == 0 and n_graphs >= 1, "the graph path was not exercised"
+    assert len(with_graphs) == len(direct)
+    for k, (a, b) in enumerate(zip(with_graphs, direct)):
+        assert a == b, f"launch {k} differs:\n{a}\n{b}\n{src}"
