@@ -273,3 +273,31 @@ def test_graph_replay_issues_exactly_the_direct_launch_sequence(monkeypatch, tmp
     assert len(with_graphs) == len(direct)
     for k, (a, b) in enumerate(zip(with_graphs, direct)):
         assert a == b, f"launch {k} differs:\n{a}\n{b}\n{src}"
+
+
+def test_cavity_pressure_loop_runs_fused_pairs_with_an_even_number_of_swaps(rt):
+    """50 Jacobi iterations = 24 fused two-sweep passes + 2 single sweeps (an even number of level-0/scratch
+    swaps per call keeps the buffer arrangement -- and the recorded graph -- on a period of two calls)."""
+    k = W.make_kernels()["cavity_kernel"]
+    nn = 1024
+    mb, mp, mu, mv = W.cavity_masks(nn, nn)
+    gs = [xgrid.Grid((nn, nn), float) for _ in range(4)]
+    for g, m in zip(gs, (mb, mp, mu, mv)):
+        g.boundary[...] = m
+    cfg = W.Config(1.0, 0.1, 1e-4, 2.0 / (nn - 1), 2.0 / (nn - 1))
+    k(*gs, cfg)
+    names = rt.names()
+    fused = [x for x in names if "jacobi2" in x]
+    single = [x for x in names if x.startswith("xg_cavity_kernel_g6_") and "jacobi2" not in x]
+    sparse = [x for x in names if x.endswith("_sparse_v1")]
+    assert len(fused) == 24 and len(single) == 2, (len(fused), len(single))
+    # boundary statements: 4 before the loop, 4 after each fused pass (those between its two sweeps are resolved
+    # on chip), 4 after each single sweep
+    assert len(sparse) == 4 + 24 * 4 + 2 * 4
+    arrangement = [g._arrangement() for g in gs]
+    k(*gs, cfg)
+    k(*gs, cfg)
+    assert [g._arrangement() for g in gs] == arrangement       # period two
+    for _ in range(4):
+        k(*gs, cfg)
+    assert len(rt.graphs) == 2
