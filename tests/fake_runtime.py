@@ -31,6 +31,7 @@ class FakeRuntime(shim.Runtime):
         self.capturing = None
         self.graphs: dict = {}
         self.functions: dict = {}
+        self.modules: dict = {}
         self.handles = 100
         self.copies: list = []
         self.real_allocs = self.real_frees = 0
@@ -110,9 +111,13 @@ class FakeRuntime(shim.Runtime):
     # ---- modules
     def module_load(self, image: bytes) -> int:
         assert image[:4] == b"\x7fELF"
-        return self._handle()
+        h = self._handle()
+        self.modules[h] = image
+        return h
 
     def get_function(self, module: int, name: str) -> int:
+        # cuModuleGetFunction fails for a kernel that is not in THIS module: check the cubin's symbol text
+        assert (".text." + name).encode() in self.modules[module], f"kernel {name} is not in the module it is looked up in"
         h = self._handle()
         self.functions[h] = name
         return h

@@ -105,6 +105,10 @@ def test_cavity_call_structure_and_graph(rt):
     sparse = [x for x in first if x.endswith("_sparse_v1")]
     # b, p-first, 4 BCs, 50 x (Jacobi + 4 BCs), fused tail (u, v, 3 Dirichlet BCs in ONE launch)
     assert len(first) == 1 + 1 + 4 + 50 * 5 + 1 and len(sparse) == 4 + 50 * 4, (len(first), len(sparse))
+    # lazy JIT: one module per generated kernel, compiled and loaded on first launch -- 57 kernels are
+    # generated for this program, one call on this grid size needs only these
+    generated = k._program().source.count('extern "C" __global__')
+    assert generated > 50 and len(rt.modules) == len(set(first)) <= 20
     n1 = len(rt.launches)
     k(*gs, cfg)
     k(*gs, cfg)

@@ -187,6 +187,9 @@ def hoist_lines(hoist: dict, indent: str = "    ") -> list:
 
 
 # --------------------------------------------------------------------------- module
+_KERNEL_NAME = __import__("re").compile(r'extern "C" __global__ void (?:__launch_bounds__\([^)]*\) )?(\w+)\(')
+
+
 class ModuleBuilder:
     """Accumulates one CUDA translation unit: struct definitions, ``__device__``
     helpers for called operators, and one or more sweep kernels."""
@@ -290,6 +293,27 @@ class ModuleBuilder:
         parts.extend(self.functions.values())
         parts.extend(self.kernels)
         return "\n".join(parts)
+
+    def chunks(self, n: int) -> list:
+        """The translation unit split into `n` independent ones for parallel compilation:
+        [(kernel names, source)].  Every chunk carries all declarations (user structs, callee
+        functions, parameter structs, inline-block prelude) in their original order and a share of
+        the kernels, balanced by text length -- kernels only depend on declarations, never on each
+        other."""
+        shared = ['#include "xgb_stencil.cuh"\n', *self.structs.values(), *self.functions.values()]
+        kernels = []
+        for text in self.kernels:
+            names = _KERNEL_NAME.findall(text)
+            if names:
+                kernels.append((names, text))
+            else:
+                shared.append(text)
+        n = max(1, min(n, len(kernels)))
+        bins = [([], [], 0) for _ in range(n)]
+        for names, text in sorted(kernels, key=lambda k: -len(k[1])):
+            k = min(range(n), key=lambda i: bins[i][2])
+            bins[k] = (bins[k][0] + names, bins[k][1] + [text], bins[k][2] + len(text))
+        return [(names, "\n".join(shared + texts)) for names, texts, _ in bins if names]
 
 
 # --------------------------------------------------------------------------- group analysis

@@ -24,6 +24,8 @@ from __future__ import annotations
 import hashlib
 import math
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import astuple, is_dataclass
 
 import numpy as np
@@ -398,6 +400,20 @@ def multistep_launches(count: int, T: int, S: int, tail: bool = True) -> tuple[l
     return steps, left
 
 
+JIT_MODE = os.environ.get("XGB_JIT", "lazy")                    # "lazy": one module per generated kernel, on first launch
+JIT_THREADS = int(os.environ.get("XGB_JIT_THREADS", "8"))      # parallel NVRTC compilations in Program.images()
+_nvrtc_warm = False
+
+
+def _warm_nvrtc() -> None:
+    """The runtime resolves libnvrtc on its first compilation; do that once before threads race for it."""
+    global _nvrtc_warm
+    if not _nvrtc_warm:
+        from ..runtime import shim
+        shim.compile_cuda('extern "C" __global__ void xgb_warm() {}', "warm.cu", ["--gpu-architecture=sm_100a"], {})
+        _nvrtc_warm = True
+
+
 def flush_pending() -> None:
     """Execute the deferred run of identical kernel calls, T time steps per launch."""
     global _PENDING
@@ -463,7 +479,10 @@ class Program:
             self.module_builder.kernels.append(text)
             self.inlines[id(st)] = ik
         self.source = self.module_builder.source() if (self.groups or self.inlines) else ""
-        self._module = None
+        self._modules: dict = {}          # unit index -> loaded module
+        self._where = None                # kernel name -> unit index
+        self._unit_list = None            # [(kernel names, source)]
+        self._cubins: list = []
         self._functions: dict = {}
         # temporal blocking: the whole kernel is scalar prologue + ONE 1-D group on one grid
         self.batchable = False
@@ -521,38 +540,83 @@ class Program:
                 self._match_pairs(node[3])
 
     # ---- JIT (replaces Compiler.compile's md5 cache, xgrid/util/ffi.py:67-85)
+    def _compile_cached(self, source: str, label: str) -> bytes:
+        """One NVRTC compilation through the on-disk cache (sha256 of source + flags + template headers)."""
+        from ..runtime import shim
+        headers = template_headers()
+        flags = self.config.nvrtc_flags
+        key = hashlib.sha256("\0".join([source, *flags, *headers.values()]).encode()).hexdigest()[:32]
+        root = os.path.join(".", self.config.cacheroot)
+        os.makedirs(root, exist_ok=True)
+        cu, cubin = os.path.join(root, key + ".cu"), os.path.join(root, key + ".cubin")
+        if os.path.exists(cubin) and os.path.exists(cu):
+            with open(cubin, "rb") as f:
+                image = f.read()
+            self.logger.info(f"jit loaded '{cubin}' from cache")
+            return image
+        image, log = shim.compile_cuda(source, label + ".cu", flags, headers)
+        tmp = f"{cu}.{os.getpid()}.{threading.get_ident()}.tmp"
+        with open(tmp, "w") as f:
+            f.write("// nvrtc " + " ".join(flags) + "\n" + source)
+        os.replace(tmp, cu)
+        tmp = f"{cubin}.{os.getpid()}.{threading.get_ident()}.tmp"
+        with open(tmp, "wb") as f:
+            f.write(image)
+        os.replace(tmp, cubin)
+        self.logger.info(f"jit compiled '{cu}' to '{cubin}'")
+        return image
+
     def image(self) -> bytes:
+        """The whole translation unit as ONE sm_100a cubin (tools, tests, the build check)."""
         if self._image is None:
-            from ..runtime import shim
-            headers = template_headers()
-            flags = self.config.nvrtc_flags
-            key = hashlib.sha256("\0".join([self.source, *flags, *headers.values()]).encode()).hexdigest()[:32]
-            root = os.path.join(".", self.config.cacheroot)
-            os.makedirs(root, exist_ok=True)
-            cu, cubin = os.path.join(root, key + ".cu"), os.path.join(root, key + ".cubin")
-            if os.path.exists(cubin) and os.path.exists(cu):
-                with open(cubin, "rb") as f:
-                    self._image = f.read()
-                self.logger.info(f"jit loaded '{cubin}' from cache")
-            else:
-                self._image, log = shim.compile_cuda(self.source, self.op.name + ".cu", flags, headers)
-                with open(cu, "w") as f:
-                    f.write("// nvrtc " + " ".join(flags) + "\n" + self.source)
-                tmp = cubin + f".{os.getpid()}.tmp"
-                with open(tmp, "wb") as f:
-                    f.write(self._image)
-                os.replace(tmp, cubin)
-                self.logger.info(f"jit compiled '{cu}' to '{cubin}'")
+            self._image = self._compile_cached(self.source, self.op.name)
         return self._image
+
+    def _units(self) -> list:
+        """[(kernel names, source)]: the compilation units of the launch path.  JIT mode "lazy" (default): one
+        unit per kernel, compiled when the kernel is first launched -- a kernel with many statements has dozens
+        of generated variants (cavity: 57 kernels, 20 s in one NVRTC call, 6 s of it for each of two variants
+        that large grids never use), while one call needs about a dozen of them.  Kernels depend only on the
+        shared declarations, never on each other, and are compiled function by function either way, so the
+        machine code is the same.  Mode "unit" (XGB_JIT=unit): the whole kernel as one module."""
+        if self._unit_list is None:
+            n = self.source.count('extern "C" __global__') if JIT_MODE == "lazy" else 1
+            self._unit_list = self.module_builder.chunks(max(1, n))
+            self._where = {k: i for i, (names, _) in enumerate(self._unit_list) for k in names}
+            self._cubins = [None] * len(self._unit_list)
+        return self._unit_list
+
+    def _unit_image(self, index: int) -> bytes:
+        units = self._units()
+        if self._cubins[index] is None:
+            names, source = units[index]
+            whole = len(units) == 1
+            self._cubins[index] = self.image() if whole else self._compile_cached(source, f"{self.op.name}.{names[0]}")
+        return self._cubins[index]
+
+    def images(self) -> list:
+        """[(kernel names, cubin)] of EVERY unit, compiled now, in parallel threads (NVRTC compiles distinct
+        programs concurrently; ctypes releases the GIL).  The build step uses it to fill the on-disk cache."""
+        units = self._units()
+        todo = [i for i in range(len(units)) if self._cubins[i] is None]
+        threads = min(JIT_THREADS, os.cpu_count() or 1, len(todo))
+        if threads > 1:
+            _warm_nvrtc()
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(self._unit_image, todo))
+        return [(names, self._unit_image(i)) for i, (names, _) in enumerate(units)]
 
     def function(self, name: str, dynamic_smem: int = 0) -> int:
         fn = self._functions.get(name)
         if fn is None:
             from ..runtime.shim import Runtime
             rt = Runtime.get()
-            if self._module is None:
-                self._module = rt.module_load(self.image())
-            fn = rt.get_function(self._module, name)
+            self._units()
+            unit = self._where[name]
+            module = self._modules.get(unit)
+            if module is None:                  # compiled (or read from the cache) and loaded on first use
+                module = self._modules[unit] = rt.module_load(self._unit_image(unit))
+            fn = rt.get_function(module, name)
             if dynamic_smem > 48 * 1024:
                 rt.set_dynamic_smem(fn, dynamic_smem)
             self._functions[name] = fn
