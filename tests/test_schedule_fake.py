@@ -305,3 +305,17 @@ def test_cavity_pressure_loop_runs_fused_pairs_with_an_even_number_of_swaps(rt):
     for _ in range(4):
         k(*gs, cfg)
     assert len(rt.graphs) == 2
+
+
+def test_unit_jit_mode_loads_one_module_per_program(rt, monkeypatch):
+    from xgrid_b200.lang import schedule
+    monkeypatch.setattr(schedule, "JIT_MODE", "unit")         # XGB_JIT=unit
+    k = W.make_kernels()["diffusion_2d"]
+    u = xgrid.Grid((64, 96), float)
+    u.boundary[0, :] = 1
+    for _ in range(3):
+        k(u, 0.2)
+    v = xgrid.Grid((128, 2048), float)                        # another variant of the same program
+    k(v, 0.2)
+    xgrid.flush()
+    assert len(set(rt.names())) >= 2 and len(rt.modules) == 1
