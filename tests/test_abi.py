@@ -81,3 +81,27 @@ def test_no_generated_workload_kernel_spills(tmp_path):
             seen += 1
             assert local == 0 and regs <= 255 and stack <= 64, (name, m.group(0))
     assert seen >= 100
+
+
+def test_per_kernel_units_give_the_same_machine_code_as_one_unit(tmp_path):
+    """Lazy JIT compiles every generated kernel as its own NVRTC unit; the SASS of the hot kernels must be
+    instruction for instruction what the whole program compiled as one unit gives."""
+    import subprocess
+    import xgrid_b200 as xgrid
+    from xgrid_b200 import workloads as W
+    from xgrid_b200.lang.schedule import Program
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+
+    def sass(path, fn):
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, str(path)], capture_output=True, text=True).stdout
+        return [re.sub(r"/\*[0-9a-f]+\*/", "", line).strip() for line in out.splitlines()
+                if re.match(r"\s+/\*[0-9a-f]{4}\*/", line)]
+
+    for workload, fn in (("convection_1d", "xg_convection_1d_g0_multistep_v1"), ("heat_3d", "xg_heat_3d_g0_tiled_v2")):
+        prog = Program(W.make_kernels()[workload])
+        whole, unit = tmp_path / "whole.cubin", tmp_path / "unit.cubin"
+        whole.write_bytes(prog.image())
+        prog._units()
+        unit.write_bytes(prog._unit_image(prog._where[fn]))
+        a, b = sass(whole, fn), sass(unit, fn)
+        assert len(a) > 300 and a == b, fn
