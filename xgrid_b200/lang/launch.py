@@ -98,6 +98,26 @@ def tiled_geometry(shape, t: dict):
 STATS: dict = {}          # kernel variant -> launches (diagnostics / tests)
 
 
+def full_grid_variant(g: cudagen.Group, shape) -> tuple:
+    """(variant, vector width, dynamic shared memory) of a one-pass sweep of group `g` over the whole grid."""
+    cols = shape[-1]
+    variant, V, smem = cudagen.VARIANT_DENSE, 1, 0
+    vmax = max(1, TUNE["vec_bytes"] // max(s.elem.width_bytes if hasattr(s.elem, "width_bytes") else 16
+                                           for s in g.slots))
+    for cand in sorted(g.vwidths, reverse=True):
+        if cols % cand == 0 and cand <= vmax:
+            V = cand
+            break
+    t = g.tiled
+    if (t is not None and TUNE["tiled"] and cols % t["V"] == 0 and cols >= t["W"] and shape[0] >= 16
+            and (g.ndim == 2 or shape[1] >= t["TJ"])):
+        variant, V = cudagen.VARIANT_TILED, t["V"]
+        smem = t["smem"]
+    elif g.march and V > 1 and TUNE["march"] and shape[0] >= 4:
+        variant = cudagen.VARIANT_MARCH
+    return variant, V, smem
+
+
 class Launcher:
     def __init__(self, program, grids: dict) -> None:
         self.program = program
@@ -245,19 +265,7 @@ class Launcher:
                 P.list, P.count = ptr, count
         P.r_lo, P.r_hi = 0, shape[0]
         if variant == cudagen.VARIANT_DENSE:
-            vmax = max(1, TUNE["vec_bytes"] // max(s.elem.width_bytes if hasattr(s.elem, "width_bytes") else 16
-                                                   for s in g.slots))
-            for cand in sorted(g.vwidths, reverse=True):
-                if cols % cand == 0 and cand <= vmax:
-                    V = cand
-                    break
-            t = g.tiled
-            if (t is not None and TUNE["tiled"] and cols % t["V"] == 0 and cols >= t["W"] and shape[0] >= 16
-                    and (g.ndim == 2 or shape[1] >= t["TJ"])):
-                variant, V = cudagen.VARIANT_TILED, t["V"]
-                smem = t["smem"]
-            elif g.march and V > 1 and TUNE["march"] and shape[0] >= 4:
-                variant = cudagen.VARIANT_MARCH
+            variant, V, smem = full_grid_variant(g, shape)
         fn = self.program.function(cudagen.kernel_name(g, variant, V), smem)
 
         def launch_rows(lo: int, hi: int) -> None:

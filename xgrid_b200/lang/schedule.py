@@ -654,7 +654,7 @@ class Program:
                 flush_pending()
                 self._bind(args)        # type / arity errors surface at the call site
                 if not self._preloaded:
-                    self._preload_batch_kernels()
+                    self._preload_batch_kernels(grid)
                 if not grid.sharded and len(grid._spares) < (2 if self.batchable else 1):
                     # output levels of the several-steps kernels: allocate with the first deferred call, in
                     # the ghost layout the flush will ask for (a sharded grid decides that at flush time)
@@ -666,9 +666,10 @@ class Program:
             flush_pending()
         return self._call_now(args)
 
-    def _preload_batch_kernels(self) -> None:
-        """Resolve the several-steps-per-launch kernels when the first call is deferred (the driver loads a
-        kernel's code at cuModuleGetFunction), so that a later flush inside a timed region only launches."""
+    def _preload_batch_kernels(self, grid) -> None:
+        """Resolve the kernels a deferred run can launch when its FIRST call is queued: the several-steps
+        variants and the one-pass kernel that runs the remainder.  With the lazy JIT each of them is compiled
+        (or read from the cache) and loaded on first use; a flush inside a timed region should only launch."""
         self._preloaded = True
         g = self.groups[0]
         if self.batchable:
@@ -676,6 +677,9 @@ class Program:
                 self.function(cudagen.kernel_name(g, variant, 1), g.multistep["smem"])
         else:
             self.function(cudagen.kernel_name(g, cudagen.VARIANT_TILED2, g.tiled2["V"]), g.tiled2["smem"])
+        from .launch import full_grid_variant
+        variant, V, smem = full_grid_variant(g, grid.shape)
+        self.function(cudagen.kernel_name(g, variant, V), smem)
 
     def _bind(self, args):
         if _Grid is None:
