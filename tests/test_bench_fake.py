@@ -1,0 +1,43 @@
+"""bench.py's own arm dry-run on the recording fake runtime (CPU): the code path executes for every workload and
+the JSON line carries every key of the measurement contract (values are meaningless here -- nothing ran)."""
+import argparse
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench
+import fake_runtime
+
+
+class TimedFake(fake_runtime.FakeRuntime):
+    def event_elapsed_ms(self, a, b):
+        return 1.0
+
+
+@pytest.mark.parametrize("workload,shape,steps", [
+    ("conv1d", [1 << 16], 150), ("diff2d", [256, 2048], 9), ("cavity", [64, 64], 3), ("heat3d", [16, 32, 256], 4),
+    ("ewmul", None, 20),
+])
+def test_bench_line_has_the_contract_keys(monkeypatch, tmp_path, workload, shape, steps):
+    from xgrid_b200.runtime import shim
+    rt = fake_runtime.install(monkeypatch)
+    rt.__class__ = TimedFake
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))          # JIT cache and MEASURED_PEAKS lookup under tmp
+    args = argparse.Namespace(workload=workload, shape=shape, steps=steps, warmup=3, no_e2e=False, no_cpu=True,
+                              gpus=1, impl="ours", cpu_budget=1.0)
+    line = bench.run_ours(args, 0, 1)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "gpu_launches", "clocks", "e2e", "impl"):
+        assert key in line, key
+    assert line["steps"] == steps and line["warmup"] >= 3 and line["n_gpus"] == 1 and line["vs_baseline"] is None
+    assert line["dtype"] == "f64" and line["data"] == "synthetic" and "workload" in line["config"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["unit"] == "GB/s"
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert line["gpu_launches"] > 0 and shim.Runtime._instance is rt
