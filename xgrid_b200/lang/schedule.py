@@ -483,6 +483,7 @@ class Program:
         self._where = None                # kernel name -> unit index
         self._unit_list = None            # [(kernel names, source)]
         self._cubins: list = []
+        self._prefetched = False
         self._functions: dict = {}
         # temporal blocking: the whole kernel is scalar prologue + ONE 1-D group on one grid
         self.batchable = False
@@ -606,6 +607,35 @@ class Program:
                 list(pool.map(self._unit_image, todo))
         return [(names, self._unit_image(i)) for i, (names, _) in enumerate(units)]
 
+    def _prefetch(self, grids: dict) -> None:
+        """First call of a program: compile the units this call is about to launch in PARALLEL threads
+        (only compilation -- modules are still loaded by `function` on first use).  The prediction repeats
+        the launcher's variant choice; a miss merely falls back to compiling that kernel when it is needed."""
+        self._prefetched = True
+        if JIT_MODE != "lazy" or not self.source:
+            return
+        from .launch import full_grid_variant
+        units = self._units()
+        names = set()
+        for g in self.groups:
+            lead = grids.get(g.lead)
+            if lead is None or lead.size == 0:
+                continue
+            if g.sparse:
+                names.add(cudagen.kernel_name(g, cudagen.VARIANT_SPARSE, 1))
+            else:
+                variant, V, _ = full_grid_variant(g, lead.shape)
+                names.add(cudagen.kernel_name(g, variant, V))
+        for pair in self.pairs.values():
+            names.add(cudagen.kernel_name(pair.sweep, jacobi2.VARIANT, pair.config["V"]))
+        names.update(ik.name for ik in self.inlines.values())
+        todo = sorted({self._where[n] for n in names if n in self._where and self._cubins[self._where[n]] is None})
+        threads = min(JIT_THREADS, os.cpu_count() or 1, len(todo))
+        if threads > 1 and len(units) > 1:
+            _warm_nvrtc()
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(self._unit_image, todo))
+
     def function(self, name: str, dynamic_smem: int = 0) -> int:
         fn = self._functions.get(name)
         if fn is None:
@@ -709,6 +739,8 @@ class Program:
     def _call_now(self, args):
         sig = self._sig
         env, grids = self._bind(args)
+        if not self._prefetched:
+            self._prefetch(grids)
         # tick the field and resize the time ring (xgrid/lang/operator.py:37-39)
         for (name, t), a in zip(sig, args):
             if isinstance(t, GridT):
