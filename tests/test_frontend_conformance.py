@@ -61,3 +61,21 @@ def test_case_matches_reference(tmp_path, name):
         assert got["depth"] == want["depth"]
         if want["ret"] is not None and not (want["ret"] == 0 and got["ret"] is None):    # void: ctypes gives 0
             assert got["ret"] == want["ret"] and type(got["ret"]) is type(want["ret"])
+
+
+def test_every_accepted_grid_kernel_compiles_unit_by_unit(tmp_path):
+    """The launch path compiles each generated kernel as its own NVRTC unit (lazy JIT): every unit of every
+    accepted grid kernel -- struct-element grids, dataclass methods, called operators, inline C, shape() --
+    must compile for sm_100a on its own (declarations are shared, kernels never depend on each other)."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+    units = 0
+    for name in sorted(FC.CASES):
+        if not GOLD[name]["ok"] or name in FC.DEVIATIONS:
+            continue
+        prog = Program(_load(name, str(tmp_path)).k)
+        if not prog.source:
+            continue                                  # scalar-only kernel: nothing runs on the device
+        for names, image in prog.images():
+            assert image[:4] == b"\x7fELF", (name, names)
+            units += 1
+    assert units >= 80
