@@ -615,7 +615,6 @@ class Program:
         if JIT_MODE != "lazy" or not self.source:
             return
         from .launch import full_grid_variant
-        units = self._units()
         names = set()
         for g in self.groups:
             lead = grids.get(g.lead)
@@ -629,6 +628,11 @@ class Program:
         for pair in self.pairs.values():
             names.add(cudagen.kernel_name(pair.sweep, jacobi2.VARIANT, pair.config["V"]))
         names.update(ik.name for ik in self.inlines.values())
+        self._compile_named(names)
+
+    def _compile_named(self, names) -> None:
+        """Compile the units of the given kernels in parallel threads (no-op for units already compiled)."""
+        units = self._units()
         todo = sorted({self._where[n] for n in names if n in self._where and self._cubins[self._where[n]] is None})
         threads = min(JIT_THREADS, os.cpu_count() or 1, len(todo))
         if threads > 1 and len(units) > 1:
@@ -702,14 +706,18 @@ class Program:
         (or read from the cache) and loaded on first use; a flush inside a timed region should only launch."""
         self._preloaded = True
         g = self.groups[0]
-        if self.batchable:
-            for variant in (cudagen.VARIANT_MULTISTEP, cudagen.VARIANT_MULTISTEP_TAIL):
-                self.function(cudagen.kernel_name(g, variant, 1), g.multistep["smem"])
-        else:
-            self.function(cudagen.kernel_name(g, cudagen.VARIANT_TILED2, g.tiled2["V"]), g.tiled2["smem"])
         from .launch import full_grid_variant
         variant, V, smem = full_grid_variant(g, grid.shape)
-        self.function(cudagen.kernel_name(g, variant, V), smem)
+        wanted = [(cudagen.kernel_name(g, variant, V), smem)]
+        if self.batchable:
+            wanted += [(cudagen.kernel_name(g, v, 1), g.multistep["smem"])
+                       for v in (cudagen.VARIANT_MULTISTEP, cudagen.VARIANT_MULTISTEP_TAIL)]
+        else:
+            wanted.append((cudagen.kernel_name(g, cudagen.VARIANT_TILED2, g.tiled2["V"]), g.tiled2["smem"]))
+        if JIT_MODE == "lazy":
+            self._compile_named([name for name, _ in wanted])
+        for name, dynamic_smem in wanted:
+            self.function(name, dynamic_smem)
 
     def _bind(self, args):
         if _Grid is None:
