@@ -6,7 +6,7 @@
 # test selection is small and every pass is bounded by `timeout`.
 O=gpurun_out
 mkdir -p $O
-SEL='tests/test_parity_gpu.py -k "golden_1d or golden_2d or multistep_tail or oracle_diff2d or golden_overstep"'
+SEL='tests/test_parity_gpu.py -k "golden_single_grid or multistep_tail or oracle_diff2d or golden_overstep"'
 for tool in memcheck racecheck synccheck; do
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 --log-file $O/sanitize_$tool.log \
       python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitize_${tool}_smoke.out 2>&1
