@@ -272,3 +272,22 @@ def test_multistep_tail_variant_is_generated():
     src = prog.source
     assert "xg_convection_1d_g0_multistep_v1(" in src and "xg_convection_1d_g0_multistep_tail_v1(" in src
     assert "round < (int)p.opt0 / S" in src and "round < T / S" in src
+
+
+def test_device_code_is_the_gpu_validated_one(tmp_path):
+    """The CUDA C generated for every workload kernel, the template headers and the NVRTC flags are the ones
+    that last went through the GPU suite on a B200 (tests/golden/codegen_hashes.json).  A session without GPU
+    access must not change device code; a session with it regenerates the file after `pytest -m gpu`
+    (tests/golden/make_codegen_hashes.py)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_codegen_hashes", os.path.join(here, "golden", "make_codegen_hashes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(here, "golden", "codegen_hashes.json")) as f:
+        want = json.load(f)
+    got = mod.hashes(str(tmp_path / "xg"))
+    changed = sorted(k for k in set(want) | set(got) if want.get(k) != got.get(k))
+    assert not changed, f"device code changed since its last GPU validation: {changed}"
