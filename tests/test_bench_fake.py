@@ -41,3 +41,23 @@ def test_bench_line_has_the_contract_keys(monkeypatch, tmp_path, workload, shape
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert line["gpu_launches"] > 0 and shim.Runtime._instance is rt
+
+
+def test_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` (the reference's own CPU kernels from oracle/_ref, else the oracle port) prints the
+    contract's line with impl=reference, a cpu_baseline describing the run and an e2e that repeats its value."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--shape", "65536",
+                          "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "stencil Gpoint-updates/s" and line["steps"] == 3
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit without work
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=120, cwd=str(tmp_path), env=env)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
