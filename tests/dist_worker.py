@@ -115,7 +115,7 @@ def main():
         # HaloPlan: a stale level of a sharded grid read at axis-0 offset 1 must be exchanged once
         lv = g._ring[0]
         assert xdist.HaloPlan.stale([(g, lv, 1), (g, lv, 1), (g, lv, 0)]) == [(g, lv, 1)]
-        lv.halo_ok = True
+        lv.halo_rows = 1
         assert xdist.HaloPlan.stale([(g, lv, 1)]) == []
         # slab-decomposed oracle run with gloo ghost exchange == single-domain oracle
         h = HostGrid((hi - lo,) + gshape[1:])

@@ -56,7 +56,8 @@ class FakeRuntime(shim.Runtime):
     def free(self, ptr: int) -> None:
         nbytes = self._sizes.pop(ptr, 0)
         self.live.pop(ptr, None)
-        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP and self._pooling():
+        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP:
+            self._fence_comm()
             self._pool.setdefault(nbytes, []).append(ptr)
             self._pool_bytes += nbytes
         else:
@@ -188,13 +189,16 @@ class FakeTransport:
     def exchange(self, items, stream=0):
         for grid, lv, h in items:
             self.log.append(("exchange", lv.dev, h, len(self.rt.launches)))
-            lv.halo_ok = True
+            lv.halo_rows = h
 
     def exchange_async(self, items):
         for grid, lv, h in items:
             self.log.append(("exchange_async", lv.dev, h, len(self.rt.launches)))
-            lv.halo_ok = True
+            lv.halo_rows = h
             lv.halo_event = self.rt.event_create()
+
+    def fence_compute(self):
+        self.log.append(("fence", 0, 0, len(self.rt.launches)))
 
     def exchange_bytes(self, data_ptr, data_bytes, halo_bytes, stream=0):
         self.log.append(("exchange_bytes", data_ptr, halo_bytes, len(self.rt.launches)))

@@ -171,6 +171,45 @@ def test_scalar_kernels_match_reference(golden):
     assert scal(1.7, 0.3, 9) == float(g["scal"])
 
 
+@dataclass
+class Pair2f:
+    x: float
+    y: float
+
+    @xgrid.function(method=True)
+    def bump(self, d: float) -> float:
+        self.x = self.x + d          # the callee's own copy (C passes structs by value)
+        return self.x
+
+
+def test_struct_values_are_copied_like_c_structs():
+    """Structs are passed, assigned and returned BY VALUE in the reference's generated C
+    (xgrid/lang/generator.py:216-225, xgrid/util/typing/value.py:103-107).  Expected values were
+    produced by running these three kernels through the unmodified reference (gcc 13.3, -O2):
+    `alias` -> 1.0, `store` -> 7.0, `method` -> 4.5, and the caller's dataclass is never modified."""
+    @xgrid.kernel()
+    def alias(p: Pair2f) -> float:
+        q = p
+        q.x = 5.0
+        return p.x
+
+    @xgrid.kernel()
+    def store(p: Pair2f) -> float:
+        p.x = 7.0
+        return p.x
+
+    @xgrid.kernel()
+    def method(p: Pair2f) -> float:
+        t = p.bump(2.5)
+        return t + p.x
+
+    p = Pair2f(1.0, 2.0)
+    assert alias(p) == 1.0 and p == Pair2f(1.0, 2.0)
+    assert store(p) == 7.0 and p == Pair2f(1.0, 2.0)
+    assert store(p) == 7.0 and p == Pair2f(1.0, 2.0)       # a repeated (replayable) call behaves the same
+    assert method(p) == 4.5 and p == Pair2f(1.0, 2.0)
+
+
 def test_c_integer_semantics():
     @xgrid.kernel()
     def idiv(a: int, b: int) -> int:

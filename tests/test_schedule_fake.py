@@ -160,9 +160,67 @@ def test_sharded_3d_sweep_runs_edges_first_and_exchanges_only_stale_levels(monke
     kinds = [e[0] for e in tr.log[before:]]
     assert kinds == ["exchange_async"], kinds
     assert rt.launches[3][3]["s1"] == written                 # ring rotated by pointer: last output is now the input
-    # the pool is bypassed while a transport exists (buffers may be in use on the communication stream)
+    # buffers of a sharded grid return to the pool too, each behind a fence that orders the compute stream
+    # after the communication stream (a halo exchange may still be reading the buffer)
+    fences = len([e for e in tr.log if e[0] == "fence"])
     del u
-    assert rt._pool_bytes == 0
+    assert rt._pool_bytes > 0                                 # (buffers under 1 MiB are freed for real)
+    assert len([e for e in tr.log if e[0] == "fence"]) > fences
+
+
+def test_halo_freshness_tracks_the_exchanged_depth(monkeypatch, tmp_path):
+    """A level exchanged at depth 1 is stale for a later group that reads it two rows across the slab
+    boundary (round-1 advisor finding: freshness was a bool)."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def two_reaches(u: f2, v: f2, w: f2) -> None:
+        v[0, 0] = u[1, 0] + u[-1, 0]
+        w[0, 0] = v[0, 0][0] + u[2, 0] + u[-2, 0]
+
+    u, v, w = (xgrid.Grid((4 * 32, 48), float) for _ in range(3))
+    u.now[...] = 1.0
+    two_reaches(u, v, w)
+    src = u._ring[1]
+    depths = [e[2] for e in tr.log if e[0] == "exchange" and e[1] == src.dev]
+    assert depths == [1, 2], tr.log                # refreshed again, deeper, before the second sweep
+    assert src.halo_rows == 2 and u._ghost >= 2
+
+
+def test_sharded_1d_run_gets_its_halo_layout_with_the_first_deferred_call(monkeypatch, tmp_path):
+    """A 1-D slab imports H points of both ring levels per multi-step launch: the ghost band is sized when the
+    first call is deferred (levels still on the host -> no copy at all), so the flush neither re-lays-out nor
+    allocates; a single-step remainder (exchanged at depth 1) leaves the level stale for the next H-deep launch."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    k = W.make_kernels()["convection_1d"]
+    u = xgrid.Grid((4 << 16,), float)
+    u.now[...] = 1.0
+    H = k._program().groups[0].multistep["H"]
+    k(u, 1.0, 0.5, 1.0)
+    assert u._ghost == H and len(u._spares) == 2 and rt.copies == []
+    for _ in range(19):
+        k(u, 1.0, 0.5, 1.0)
+    allocs = rt.real_allocs
+    xgrid.flush()
+    assert [c[0] for c in rt.copies] == ["h2d"] and rt.real_frees == 0      # upload of the IC; nothing else moves
+    assert rt.real_allocs - allocs <= 4                                     # level 0/1 + mask + flags, no re-layout
+    names = rt.names()
+    assert names[0].endswith("multistep_tail_v1") and rt.launches[0][3]["opt0"] == 20
+    assert [e[2] for e in tr.log if e[0] == "exchange"] == [H, H]           # both ring levels, H deep
+    # second run of 21: tail launch of 20 + one single step; the single step's depth-1 exchange must not
+    # pass for fresh when the next multi-step launch asks for H
+    for _ in range(21):
+        k(u, 1.0, 0.5, 1.0)
+    xgrid.flush()
+    n = len(tr.log)
+    for _ in range(20):
+        k(u, 1.0, 0.5, 1.0)
+    xgrid.flush()
+    assert sorted(e[2] for e in tr.log[n:] if e[0] == "exchange") == [H, H]
+    assert rt.real_frees == 0
 
 
 def test_sharded_overstep_sets_open_flags_from_the_topology(monkeypatch, tmp_path):
@@ -237,8 +295,8 @@ def test_ghost_relayout_drops_and_rebuilds_device_buffers(rt):
     first = {lv.raw for lv in u._ring}
     far(u)                                                    # needs 3 ghost rows: levels are re-laid-out
     assert u._ghost == 3 and first.isdisjoint({lv.raw for lv in u._ring})
-    downloads = [c for c in rt.copies if c[0] == "d2h"]
-    assert len(downloads) == 2                                # both device levels came back to the host first
+    moved = [c[0] for c in rt.copies if c[0] in ("d2h", "d2d")]
+    assert moved == ["d2d", "d2d"]                            # re-laid-out on the device, no host round trip
     near(u)                                                   # a smaller halo keeps the larger layout
     assert u._ghost == 3
 
@@ -319,3 +377,52 @@ def test_unit_jit_mode_loads_one_module_per_program(rt, monkeypatch):
     k(v, 0.2)
     xgrid.flush()
     assert len(set(rt.names())) >= 2 and len(rt.modules) == 1
+
+
+def test_writes_through_a_retained_boundary_array_are_seen(rt):
+    """`.boundary` is a plain attribute in the reference (xgrid/xgrid/__init__.py:41): `b = g.boundary`
+    kept across kernel calls and written later must reach the next call; queued (deferred) calls must
+    still run with the mask they were called with."""
+    k = W.make_kernels()["diffusion_1d"]
+    u = xgrid.Grid((4096,), float)                            # below the deferral threshold
+    b = u.boundary
+    b[0] = 1
+    k(u, 0.01, 0.1, 1.0)
+    v1 = u._mask_version
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1                              # untouched: no re-compare, no re-upload
+    b[-1] = 1                                                 # through the retained array
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1 + 1 and u._mask_snapshot[-1] == 1
+    b += 0                                                    # in-place operator: touched, but unchanged
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1 + 1
+    np.copyto(b, np.zeros(4096, np.int32))
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1 + 2 and not u._mask_any
+    # deferred run: the write flushes the queued calls first
+    w = xgrid.Grid((1 << 16,), float)
+    bw = w.boundary
+    bw[0] = 1
+    for _ in range(10):
+        k(w, 0.01, 0.1, 1.0)
+    n = len(rt.launches)
+    bw[5] = 1
+    assert len(rt.launches) > n                               # the 10 queued steps ran with the old mask
+    assert isinstance(b == 1, np.ndarray) and type(b == 1) is np.ndarray
+
+
+def test_writes_through_a_retained_now_array_reach_the_device(rt):
+    k = W.make_kernels()["diffusion_1d"]
+    u = xgrid.Grid((4096,), float)
+    a = u.now
+    a[...] = 1.0
+    k(u, 0.01, 0.1, 1.0)                                      # `a` now mirrors ring level 1 (device-resident)
+    lv = u._ring[1]
+    assert lv.host is not None and lv.where == "device"
+    copies = len(rt.copies)
+    a[7] = 3.0                                                # kept array, written after the call
+    assert lv.where == "host" and rt.copies[copies:] == [("d2h", lv.dev, 4096 * 8)]
+    k(u, 0.01, 0.1, 1.0)
+    assert ("h2d", lv.dev, 4096 * 8) in rt.copies[copies:]    # uploaded again before the sweep
+    assert u.now is u.now

@@ -85,21 +85,25 @@ def reset() -> None:
 class HaloPlan:
     """Which levels need their ghost rows refreshed before a group runs.
 
-    ``needs(group_slots, levels)`` is pure bookkeeping: a level is stale when it
-    has been written or uploaded since its last exchange (``_Level.halo_ok``)."""
+    Pure bookkeeping: ``_Level.halo_rows`` is the number of ghost rows (counted from the
+    slab outwards) that hold the neighbours' current rows -- 0 after the level has been
+    written or uploaded.  A read that reaches ``h`` rows across the slab boundary finds the
+    level stale when ``halo_rows < h``: a level exchanged at depth 1 is NOT fresh for a
+    later group that reads it at depth 2."""
 
     @staticmethod
     def stale(reads: list) -> list:
         """reads: [(grid, level_object, halo_rows)] -> the subset to exchange."""
-        out, seen = [], set()
+        want: dict = {}
         for grid, lv, h in reads:
             if h <= 0 or not getattr(grid, "sharded", False):
                 continue
-            if getattr(lv, "halo_ok", False) or id(lv) in seen:
+            if getattr(lv, "halo_rows", 0) >= h:
                 continue
-            seen.add(id(lv))
-            out.append((grid, lv, h))
-        return out
+            hit = want.get(id(lv))
+            if hit is None or hit[2] < h:          # several reads of one level: the deepest one decides
+                want[id(lv)] = (grid, lv, h)
+        return list(want.values())
 
 
 class NcclTransport:
@@ -163,6 +167,14 @@ class NcclTransport:
         for _, lv, _ in items:
             lv.halo_event = done
 
+    def fence_compute(self) -> None:
+        """Order the compute stream behind everything enqueued on the comm stream so far (device-side
+        wait only): called before a buffer a halo exchange may still be reading is recycled."""
+        if self._comm_stream is not None:
+            ev = self._event()
+            self.rt.event_record_raw(ev, self._comm_stream)
+            self.rt.stream_wait_event(0, ev)
+
     def _event(self) -> int:
         """Round-robin pool of events (an event is reused long after its waiters ran)."""
         if len(self._events) < 64:
@@ -195,8 +207,8 @@ class NcclTransport:
             d.send_hi = lv.dev + (n0 - h) * row    # my last h rows   -> rank+1's lower ghost
             d.recv_hi = lv.dev + n0 * row          # my upper ghost   <- rank+1's first h rows
         self.shim.check(self.shim.lib().xgb_halo_exchange(descs, len(items), stream))
-        for _, lv, _ in items:
-            lv.halo_ok = True
+        for _, lv, h in items:
+            lv.halo_rows = h
 
 
 def transport():

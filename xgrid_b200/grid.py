@@ -24,6 +24,7 @@ import ctypes
 
 import numpy as np
 
+from . import hostview
 from .log import Logger
 from .types import Grid as GridT, Structure, Value, parse_annotation
 
@@ -55,17 +56,18 @@ def parse_numpy_dtype(t: Value):
 
 class _Level:
     """One time level: device allocation + optional host mirror."""
-    __slots__ = ("dev", "host", "where", "raw", "halo_ok", "halo_event", "pinned", "xfers")
+    __slots__ = ("dev", "host", "where", "raw", "halo_rows", "halo_event", "pinned", "xfers", "view")
 
     def __init__(self, host=None) -> None:
         self.dev = 0            # device pointer of the first *real* element (0 = not allocated)
         self.host = host        # np.ndarray or None (an all-zero level never touched by the host)
         self.where = "host" if host is not None else "zero"
         self.raw = 0            # base of the padded device allocation
-        self.halo_ok = False    # ghost rows hold the neighbours' current rows (sharded grids)
+        self.halo_rows = 0      # ghost rows (this many, next to the slab) hold the neighbours' current rows; 0 = stale
         self.pinned = 0         # address of the page-locked host mirror (0 = pageable)
         self.halo_event = 0     # event of a halo exchange still in flight on the comm stream
         self.xfers = 0          # address of the mirror that has been transferred once (pin on 2nd use)
+        self.view = None        # (mirror, write-tracking view of it) handed out by .now / _data
 
 
 class Grid:
@@ -103,6 +105,7 @@ class Grid:
         self._scratch: _Level | None = None
         self._spares: list[_Level] = []
         self._boundary = np.zeros(self.shape, dtype=np.int32)
+        self._boundary_view = None
         self._mask_touched = True
         self._mask_snapshot = None
         self._mask_raw = 0
@@ -128,7 +131,33 @@ class Grid:
     def boundary(self) -> np.ndarray:
         _flush()
         self._mask_touched = True
-        return self._boundary
+        if self._boundary_view is None or self._boundary_view[0] is not self._boundary:
+            self._boundary_view = (self._boundary, hostview.make(self._boundary, self._mask_written))
+        return self._boundary_view[1]
+
+    def _mask_written(self, view=None) -> None:
+        """A write through a `.boundary` array (possibly one the program kept from earlier) is about to
+        happen: deferred calls still see the old mask, the next call re-compiles it if it changed."""
+        _flush()
+        self._mask_touched = True
+
+    def _host_written(self, view) -> None:
+        """A write through a `.now` / `_data` array is about to happen.  If the level it mirrors has newer
+        data on the device (the array was kept across kernel calls), bring that back first; the host
+        copy is the truth afterwards and the next kernel call uploads it -- like the reference, where
+        the array IS the level's storage whatever ring position it has rotated to."""
+        addr = view.__array_interface__["data"][0]
+        for lv in [*self._ring, *self._spares, *([self._scratch] if self._scratch is not None else [])]:
+            host = lv.host
+            if host is None or not (host.ctypes.data <= addr < host.ctypes.data + max(host.nbytes, 1)):
+                continue
+            if lv.where == "device":
+                _flush()
+                if lv.where == "device":
+                    self._download(lv)
+            if lv.where != "zero":
+                lv.where = "host"
+            return
 
     @boundary.setter
     def boundary(self, value) -> None:
@@ -137,6 +166,8 @@ class Grid:
         if arr.shape != self.shape:
             self.logger.dead("boundary mask has an incompatible shape")
         self._boundary = np.ascontiguousarray(arr)
+        if self._boundary is value:
+            self._boundary = self._boundary.copy()      # the caller keeps its own array
         self._mask_touched = True
 
     @property
@@ -186,7 +217,7 @@ class Grid:
         rt = self._runtime()
         rt.h2d(lv.dev + off * self.itemsize, src.ctypes.data, self.itemsize)
         rt.sync()
-        lv.halo_ok = False
+        lv.halo_rows = 0
 
     def fill(self, data: np.ndarray, time: int = 0) -> None:
         if data.shape != self.shape or data.dtype != self.numpy_dtype:
@@ -281,21 +312,27 @@ class Grid:
         if lv.where == "zero":
             lv.host = np.zeros(self.shape, self.numpy_dtype)
         elif lv.where == "device":
-            if lv.host is None:
-                lv.host = self._adopt_stale_mirror(lv)
-            if lv.host is None:
-                lv.host = np.empty(self.shape, self.numpy_dtype)
-            rt = self._runtime()
-            nbytes = self.size * self.itemsize
-            if rt.STAGED and nbytes >= rt.STAGED_MIN and not lv.pinned:
-                rt.d2h_staged(lv.host.ctypes.data, lv.dev, nbytes)      # pageable mirror, several host threads
-            else:
-                self._pin(lv)
-                rt.d2h(lv.host.ctypes.data, lv.dev, nbytes)
-            rt.sync()
+            self._download(lv)
         # the caller may write through the returned array: the host owns the level now
         lv.where = "host"
-        return lv.host
+        if lv.view is None or lv.view[0] is not lv.host:
+            lv.view = (lv.host, hostview.make(lv.host, self._host_written))
+        return lv.view[1]
+
+    def _download(self, lv: _Level) -> None:
+        """Device -> host mirror of one level (blocking)."""
+        if lv.host is None:
+            lv.host = self._adopt_stale_mirror(lv)
+        if lv.host is None:
+            lv.host = np.empty(self.shape, self.numpy_dtype)
+        rt = self._runtime()
+        nbytes = self.size * self.itemsize
+        if rt.STAGED and nbytes >= rt.STAGED_MIN and not lv.pinned:
+            rt.d2h_staged(lv.host.ctypes.data, lv.dev, nbytes)      # pageable mirror, several host threads
+        else:
+            self._pin(lv)
+            rt.d2h(lv.host.ctypes.data, lv.dev, nbytes)
+        rt.sync()
 
     def _adopt_stale_mirror(self, lv: _Level):
         """A level without a host mirror takes over the mirror of a SPARE level (a buffer that left the
@@ -333,25 +370,38 @@ class Grid:
         elif lv.where == "zero":
             self._runtime().memset(lv.dev, 0, self.size * self.itemsize)
         lv.where = "device"
-        lv.halo_ok = False
+        lv.halo_rows = 0
         lv.halo_event = 0
 
     def _ensure_ghost(self, rows: int) -> None:
+        """Widen the ghost band of every level to `rows` rows.  Device-resident levels are re-laid-out ON
+        THE DEVICE (new allocation from the pool + one device-to-device copy of the real rows, enqueued on
+        the compute stream); levels whose truth is on the host just drop their device copy and are uploaded
+        into the new layout by the next call.  Scratch and spare levels hold no live data."""
         if rows <= self._ghost:
             return
-        # re-layout: pull everything to the host, drop device copies
-        for k in range(len(self._ring)):
-            if self._ring[k].where == "device":
-                self._host_view(k)
+        self._ghost = rows
+        nbytes = self.size * self.itemsize
         for lv in self._ring:
-            self._release(lv)
+            if not lv.dev:
+                continue
+            old_raw, old_dev = lv.raw, lv.dev
+            if lv.where == "device":
+                self._alloc_level(lv)                  # zero-filled, new layout
+                self._runtime().d2d(lv.dev, old_dev, nbytes)
+            else:
+                lv.dev = lv.raw = 0
+            self._runtime().free(old_raw)
+            if old_raw in self._allocs:
+                self._allocs.remove(old_raw)
+            lv.halo_rows = 0
+            lv.halo_event = 0
         if self._scratch is not None:
             self._release(self._scratch)
             self._scratch = None
         for lv in self._spares:
             self._release(lv)
         self._spares = []
-        self._ghost = rows
 
     def _prepare_device(self, ghost_rows: int = 1) -> None:
         """Make every level and the mask resident before launches."""
@@ -471,6 +521,7 @@ class Grid:
 
     # ------------------------------------------------------------------ misc
     def device_pointer(self, level: int = 0) -> int:
+        _flush()
         return self._ring[level].dev
 
     def __del__(self) -> None:

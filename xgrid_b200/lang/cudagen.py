@@ -988,6 +988,10 @@ def multistep_config(g: Group):
     time steps per launch from shared memory."""
     if g.ndim != 1 or g.implicit or g.sparse:
         return None
+    if not any(st.sweep.mask == 0 for st in g.stmts):
+        # the register path of all-zero-mask tiles advances x{s} from x{s-1}; without a mask-0 statement
+        # those points are never written and must keep the value from TWO steps back (SURVEY.md F5)
+        return None
     grids = {s.grid for s in g.slots}
     if len(grids) != 1:
         return None

@@ -198,7 +198,7 @@ class Launcher:
                 shape[a] = n
             setattr(P, f"m_{name}", grid._mask_dev if grid._mask_any else None)
             for lv in grid._ring:          # the text may write any level
-                lv.halo_ok = False
+                lv.halo_rows = 0
                 lv.halo_event = 0
         for name, t in ik.scalars:
             if name in env and env[name] is not None:
@@ -287,6 +287,13 @@ class Launcher:
             STATS[variant] = STATS.get(variant, 0) + 1
 
         written = [(self.grids[s.grid], s) for s in g.slots if s.written]
+        for gr, s in written:
+            # a halo exchange of the level about to be overwritten may still be reading its edge rows on
+            # the comm stream (nothing read its ghost rows in between): order this sweep behind it
+            lv = gr._scratch if s.level == "scratch" else gr._ring[s.level]
+            if gr.sharded and lv is not None and lv.halo_event:
+                self.rt.stream_wait_event(0, lv.halo_event)
+                lv.halo_event = 0
         edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)
         if (edge and TUNE["overlap"] and variant in (cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH)
                 and shape[0] >= 8 * edge):
@@ -314,7 +321,7 @@ class Launcher:
             if s.written:
                 grid = self.grids[s.grid]
                 lv = grid._scratch if s.level == "scratch" else grid._ring[s.level]
-                lv.halo_ok = False
+                lv.halo_rows = 0
                 lv.halo_event = 0
 
     def _refresh_halos(self, g: cudagen.Group) -> None:
@@ -327,7 +334,7 @@ class Launcher:
             if s.read and s.halo0 > 0:
                 grid = self.grids[s.grid]
                 lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
-                if grid.sharded and lv.halo_ok and lv.halo_event:
+                if grid.sharded and lv.halo_event:
                     self.rt.stream_wait_event(0, lv.halo_event)
                     lv.halo_event = 0
                 reads.append((grid, lv, s.halo0))

@@ -21,6 +21,7 @@ identities) into a CUDA graph and replayed afterwards.
 """
 from __future__ import annotations
 
+import copy
 import hashlib
 import math
 import os
@@ -138,7 +139,9 @@ def np_type(t):
 def coerce(t, value):
     """Convert a Python / numpy value to the C object type ``t``."""
     if isinstance(t, Structure):
-        return value
+        # C passes, assigns and returns structs BY VALUE (the reference emits `struct S q = p;`,
+        # generator.py:216-225): `q = p; q.x = 5.0` must leave p -- and the caller's dataclass -- untouched
+        return copy.deepcopy(value)
     if isinstance(t, Integer):
         half = 1 << (t.width_bits - 1)
         return np_type(t)((int(value) + half) % (2 * half) - half)   # two's-complement wrap
@@ -270,7 +273,7 @@ def call_scalar_operator(op, args, grids):
     d = op.ir
     env = {}
     for (n, t), v in zip(d.signature.arguments, args):
-        env[n] = v
+        env[n] = coerce(t, v) if isinstance(t, Structure) else v      # by-value struct parameters
     runner = _Interpreter(d, env, grids, launcher=None)
     return runner.run(build_plan(d.body, [], None))
 
@@ -364,6 +367,14 @@ class _Interpreter:
         else:
             raise Exception(f"unsupported statement {type(s).__name__}")
 
+    def _designated(self, e):
+        """The struct object an lvalue expression names (`q`, `q.inner`), not a by-value copy of it."""
+        if isinstance(e, ir.Identifier) and not isinstance(e.variable.type, Pointer):
+            return self.env[e.variable.name]
+        if isinstance(e, ir.Access):
+            return getattr(self._designated(e.value), e.attribute)
+        return self.ev(e)
+
     def assign(self, target, value) -> None:
         if isinstance(target, ir.Identifier):
             var = target.variable
@@ -372,7 +383,7 @@ class _Interpreter:
             else:
                 self.env[var.name] = coerce(var.type, value)
         elif isinstance(target, ir.Access):
-            base = self.ev(target.value)
+            base = self._designated(target.value)
             setattr(base, target.attribute, _to_py(coerce(target.type, value)))
         else:
             raise Exception("unsupported assignment target")
@@ -689,11 +700,16 @@ class Program:
                 self._bind(args)        # type / arity errors surface at the call site
                 if not self._preloaded:
                     self._preload_batch_kernels(grid)
-                if not grid.sharded and len(grid._spares) < (2 if self.batchable else 1):
-                    # output levels of the several-steps kernels: allocate with the first deferred call, in
-                    # the ghost layout the flush will ask for (a sharded grid decides that at flush time)
-                    grid._ensure_ghost(1 if self.batchable else self.groups[0].tiled2["ghost"])
-                    grid._spare_levels(2 if self.batchable else 1)
+                # output levels of the several-steps kernels: allocate with the first deferred call, in
+                # the ghost layout the flush will ask for (a 1-D slab imports H points of both ring levels
+                # per launch) -- a flush inside a timed region should only launch, never re-lay-out
+                if self.batchable:
+                    need, spares = (self.groups[0].multistep["H"] if grid.sharded else 1), 2
+                else:
+                    need, spares = self.groups[0].tiled2["ghost"], 1
+                if grid._ghost < need or len(grid._spares) < spares:
+                    grid._ensure_ghost(need)
+                    grid._spare_levels(spares)
                 _PENDING = {"program": self, "args": args, "grid": grid, "key": key, "count": 1}
                 return None
         if _PENDING is not None:
@@ -739,7 +755,7 @@ class Program:
             elif isinstance(t, Structure):
                 if not is_dataclass(a):
                     raise TypeError(f"argument '{name}' expects dataclass {t.name}")
-                env[name] = a
+                env[name] = copy.deepcopy(a)          # by value: the kernel works on its own copy
             else:
                 env[name] = coerce(t, a)
         return env, grids
@@ -868,7 +884,7 @@ class Program:
                     grid._ring = [x1, x0]
                 for lv in grid._ring:
                     lv.where = "device"
-                    lv.halo_ok = False
+                    lv.halo_rows = 0
                 done += 2
         for _ in range(count - done):
             self._call_now(args)
@@ -917,7 +933,7 @@ class Program:
                 fn = self.function(cudagen.kernel_name(g, variant, 1), cfg["smem"])
                 x0, x1 = grid._ring[0], grid._ring[1]
                 if grid.sharded:
-                    stale = [(grid, lv, cfg["H"]) for lv in (x0, x1) if not lv.halo_ok]
+                    stale = [(grid, lv, cfg["H"]) for lv in (x0, x1) if lv.halo_rows < cfg["H"]]
                     if stale:
                         dist.transport().exchange(stale)
                 c, d = grid._spare_levels(2)
@@ -927,7 +943,7 @@ class Program:
                 STATS["multistep"] = STATS.get("multistep", 0) + 1
                 grid._ring, grid._spares = [c, d], [x0, x1]
                 c.where = d.where = "device"
-                c.halo_ok = d.halo_ok = False
+                c.halo_rows = d.halo_rows = 0
                 done += steps
         for _ in range(count - done):
             self._call_now(args)

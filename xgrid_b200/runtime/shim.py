@@ -152,8 +152,11 @@ class Runtime:
     # returns the pages to the driver (measured on B200: ~100 ms per freed 128 MiB level, and the next
     # cudaMalloc of that size pays again), so freed buffers of >= POOL_MIN bytes are kept by exact size and
     # handed out again zero-filled, which is what xgb_alloc guarantees.  Re-use is ordered on the compute
-    # stream (the memset is enqueued there); processes that also run a communication stream (sharded grids)
-    # bypass the pool.  The pool is dropped when an allocation fails and at most POOL_CAP bytes are kept.
+    # stream (the memset is enqueued there); in processes that also run a communication stream (sharded
+    # grids) a buffer enters the pool only after the compute stream has been ordered behind the work already
+    # enqueued on the communication stream (`fence_compute`: one event record + one stream wait, no host
+    # synchronisation), so a halo exchange still reading the buffer finishes before its next owner's memset.
+    # The pool is dropped when an allocation fails and at most POOL_CAP bytes are kept.
     POOL_MIN = 1 << 20
     POOL_CAP = int(float(os.environ.get("XGB_POOL_GB", "24")) * (1 << 30))
 
@@ -177,16 +180,18 @@ class Runtime:
 
     def free(self, ptr: int) -> None:
         nbytes = self._sizes.pop(ptr, 0)
-        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP and self._pooling():
+        if nbytes >= self.POOL_MIN and self._pool_bytes + nbytes <= self.POOL_CAP:
+            self._fence_comm()
             self._pool.setdefault(nbytes, []).append(ptr)
             self._pool_bytes += nbytes
             return
         self.l.xgb_free(c_void_p(ptr))
 
     @staticmethod
-    def _pooling() -> bool:
+    def _fence_comm() -> None:
         from .. import dist
-        return dist._transport is None
+        if dist._transport is not None:
+            dist._transport.fence_compute()
 
     def trim_pool(self) -> None:
         """Return every cached buffer to the driver."""
