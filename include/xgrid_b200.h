@@ -71,6 +71,15 @@ int xgb_mem_info(uint64_t *free_bytes, uint64_t *total_bytes);
  * xgb_h2d from a pinned buffer); xgb_d2h_staged returns when dst_host is complete. */
 int xgb_h2d_staged(void *dst_dev, const void *src_host, size_t bytes, xgb_handle stream);
 int xgb_d2h_staged(void *dst_host, const void *src_dev, size_t bytes, xgb_handle stream);
+/* Host half of the mask upload.  replaces: the reference handing the int32 `Grid.boundary` array to every
+ * sweep (xgrid/xgrid/__init__.py:41,66; tested per point, xgrid/lang/generator.py:295-298).  Packs
+ * src[0:n] (int32) into dst[0:n_padded] (one byte per point; n_padded a multiple of 128, tail zero),
+ * flags[0:n_padded/128] (1 iff any byte of the 128-point chunk is non-zero) and hist[256] (points per
+ * value) with several host threads, so that one byte per point -- not four -- crosses PCIe.  Values
+ * outside [0, 254] are stored as 255 and set *bad (255 = "outside the grid" on the device).  Pure host
+ * work: needs no GPU and no xgb_init.  threads <= 0: pick from the machine. */
+int xgb_mask_pack(const int32_t *src, size_t n, size_t n_padded, uint8_t *dst, uint8_t *flags,
+                  uint64_t *hist_256, int *bad, int threads);
 
 /* ---- streams / events --------------------------------------------------- */
 /* stream 0 is the backend's default compute stream (created by xgb_init). */

@@ -90,6 +90,15 @@ def threads() -> int:
     return int(lib().xo_threads())
 
 
+def set_threads(n: int) -> int:
+    """OpenMP team size of every kernel in this process -- the C port and the reference's own shared
+    objects under oracle/_ref share one libgomp.  Needed under torchrun, which exports
+    OMP_NUM_THREADS=1 to its workers (libgomp reads the variable once, when it is loaded)."""
+    lib()
+    C.CDLL("libgomp.so.1").omp_set_num_threads(int(max(1, n)))
+    return threads()
+
+
 # --------------------------------------------------------------------------- storage
 class HostGrid:
     """xgrid/xgrid/__init__.py:21-86 on the host, with padded level buffers."""

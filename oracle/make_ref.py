@@ -14,7 +14,7 @@ reference itself writes its generated C and the shared objects there
 (``init(precision="double", opt_level=3, parallel=True)`` -> ``gcc -shared
 -fpic -lm -fopenmp -O3``, xgrid/util/init.py:22-33).  Nothing from the
 reference's sources is copied: the kernel programs are the DSL text of
-``xgrid_b200/workloads.py`` (the README / test.py / examples programs),
+``examples/workloads.py`` (the README / test.py / examples programs),
 re-imported with ``xgrid`` bound to the reference package.
 
 ``oracle/_ref/manifest.json`` records, per kernel, the shared object, the
@@ -38,7 +38,7 @@ import numpy as np
 REF = os.environ.get("XGRID_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
-WORKLOADS = os.path.join(os.path.dirname(HERE), "xgrid_b200", "workloads.py")
+WORKLOADS = os.path.join(os.path.dirname(HERE), "examples", "workloads.py")
 
 
 def main() -> int:

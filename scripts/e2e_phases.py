@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench                                    # noqa: E402
 import xgrid_b200 as xgrid                      # noqa: E402
-from xgrid_b200 import workloads as W           # noqa: E402
+from examples import workloads as W           # noqa: E402
 from xgrid_b200.runtime.shim import Runtime     # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "conv1d"

@@ -1,7 +1,7 @@
 import sys, time, cProfile, pstats; sys.path.insert(0, "/root/repo")
 import numpy as np
 import xgrid_b200 as xgrid
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 xgrid.init(precision="double", cacheroot="/tmp/xgp")
 k = W.make_kernels()
 a, b, r = (xgrid.Grid((10000,), float) for _ in range(3))

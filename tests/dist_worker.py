@@ -20,7 +20,7 @@ import oracle
 from oracle import HostGrid
 import xgrid_b200 as xgrid
 from xgrid_b200 import dist as xdist
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 
 
 def oracle_global(shape, ic, mask, steps, a):

@@ -12,7 +12,7 @@ import ctypes
 
 import numpy as np
 
-from xgrid_b200.runtime import devmask, shim
+from xgrid_b200.runtime import shim
 
 
 class Info:
@@ -62,6 +62,11 @@ class FakeRuntime(shim.Runtime):
             self._pool_bytes += nbytes
         else:
             self.real_frees += 1
+
+    def trim_pool(self) -> None:
+        self.real_frees += sum(len(c) for c in self._pool.values())
+        self._pool.clear()
+        self._pool_bytes = 0
 
     def memset(self, ptr, byte, nbytes, stream=0):
         pass
@@ -163,17 +168,12 @@ class FakeRuntime(shim.Runtime):
         return [r[0] for r in self.launches[since:]]
 
 
-def _host_compile_mask(rt, boundary, mask_dev, flags_dev, n_padded):
-    flat = np.asarray(boundary).reshape(-1)
-    bad = bool(((flat < 0) | (flat > 254)).any())
-    return np.bincount(np.clip(flat, 0, 255), minlength=256).astype(np.int64), bad
 
 
 def install(monkeypatch) -> FakeRuntime:
     """Make FakeRuntime the process's runtime for one test (pytest's monkeypatch undoes it)."""
     rt = FakeRuntime()
     monkeypatch.setattr(shim.Runtime, "_instance", rt)
-    monkeypatch.setattr(devmask, "compile_mask", _host_compile_mask)
     from xgrid_b200.lang import launch, schedule
     monkeypatch.setattr(schedule, "_PENDING", None)
     monkeypatch.setattr(launch, "STATS", {})

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 def hashes(cacheroot: str) -> dict:
     import xgrid_b200 as xgrid
-    from xgrid_b200 import workloads as W
+    from examples import workloads as W
     from xgrid_b200.lang.schedule import Program, template_headers
     out = {}
     for mode in ("none", "wrap"):

@@ -50,7 +50,7 @@ def test_generated_kernels_use_bulk_copy_engine(tmp_path):
     + SYNCS (mbarrier) appear in the sm_100a cubin."""
     import subprocess
     import xgrid_b200 as xgrid
-    from xgrid_b200 import workloads as W
+    from examples import workloads as W
     from xgrid_b200.lang.schedule import Program
     xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
     img = Program(W.make_kernels()["heat_3d"]).image()
@@ -65,7 +65,7 @@ def test_no_generated_workload_kernel_spills(tmp_path):
     (the small stacks belong to the out-of-line slow path of the exact division)."""
     import subprocess
     import xgrid_b200 as xgrid
-    from xgrid_b200 import workloads as W
+    from examples import workloads as W
     from xgrid_b200.lang.schedule import Program
     xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
     seen = 0
@@ -88,7 +88,7 @@ def test_per_kernel_units_give_the_same_machine_code_as_one_unit(tmp_path):
     instruction for instruction what the whole program compiled as one unit gives."""
     import subprocess
     import xgrid_b200 as xgrid
-    from xgrid_b200 import workloads as W
+    from examples import workloads as W
     from xgrid_b200.lang.schedule import Program
     xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
 

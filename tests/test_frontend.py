@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import xgrid_b200 as xgrid
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 from xgrid_b200.lang import ir
 from xgrid_b200.lang.schedule import Program
 

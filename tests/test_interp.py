@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import xgrid_b200 as xgrid
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 from oracle import HostGrid
 from oracle.interp import Interp
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import xgrid_b200 as xgrid
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 from xgrid_b200.lang import jacobi2
 from xgrid_b200.lang.schedule import Program
 from oracle import HostGrid

@@ -7,7 +7,7 @@ import pytest
 
 import oracle
 from oracle import HostGrid, ref
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 
 pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (python oracle/make_ref.py)")
 

@@ -8,7 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import xgrid_b200 as xgrid
-from xgrid_b200 import workloads as W
+from examples import workloads as W
 import oracle
 from oracle import HostGrid
 

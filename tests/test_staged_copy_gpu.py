@@ -31,7 +31,7 @@ def test_staged_round_trip(tmp_path, nbytes):
 
 def test_grid_through_staged_path(tmp_path, monkeypatch):
     import xgrid_b200 as xgrid
-    from xgrid_b200 import workloads as W
+    from examples import workloads as W
     from xgrid_b200.runtime.shim import Runtime
     import oracle
     xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))

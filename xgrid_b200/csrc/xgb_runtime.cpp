@@ -187,21 +187,33 @@ struct Nccl {
 // lane's other chunk.  Correct on hardware (tests/test_staged_copy_gpu.py); opt-in from Python
 // (XGB_STAGED_COPY=1) until it has been timed against the driver's pageable path.
 namespace {
-constexpr int kStageLanes = 4;
+constexpr int kStageLanesMax = 16;
 constexpr size_t kStageChunk = size_t(4) << 20;
+// lanes in use: XGB_STAGE_LANES, default 8 (host memcpy of one thread is ~10 GB/s; PCIe 5 x16 moves ~50)
+int stage_lanes() {
+    static int n = [] {
+        const char *e = getenv("XGB_STAGE_LANES");
+        int v = e ? atoi(e) : 8;
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw && v > (int)hw) v = (int)hw;
+        return v < 1 ? 1 : (v > kStageLanesMax ? kStageLanesMax : v);
+    }();
+    return n;
+}
 struct StageLane {
     void *buf[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;
     cudaStream_t stream = nullptr;
 };
-StageLane g_lanes[kStageLanes];
+StageLane g_lanes[kStageLanesMax];
 cudaEvent_t g_stage_start = nullptr;
 std::mutex g_stage_mu;  // one staged copy at a time: the lanes are shared
 
 int stage_init() {
     if (!g_stage_start) XGB_CUDA(cudaEventCreateWithFlags(&g_stage_start, cudaEventDisableTiming));
-    for (auto &l : g_lanes) {
+    for (int i = 0; i < stage_lanes(); ++i) {
+        StageLane &l = g_lanes[i];
         if (l.stream) continue;
         for (int b = 0; b < 2; ++b) {
             XGB_CUDA(cudaHostAlloc(&l.buf[b], kStageChunk, cudaHostAllocDefault));
@@ -213,11 +225,12 @@ int stage_init() {
     return 0;
 }
 
-// Runs fn(lane index) on kStageLanes threads bound to the runtime's device; returns the first CUDA error.
+// Runs fn(lane index) on stage_lanes() threads bound to the runtime's device; returns the first CUDA error.
 template <class F>
 cudaError_t run_lanes(F fn) {
     std::atomic<int> err{(int)cudaSuccess};
     std::vector<std::thread> pool;
+    const int kStageLanes = stage_lanes();
     for (int t = 0; t < kStageLanes; ++t)
         pool.emplace_back([&, t] {
             cudaError_t e = cudaSetDevice(g_device);
@@ -371,7 +384,8 @@ int xgb_h2d_staged(void *dst_dev, const void *src_host, size_t bytes, xgb_handle
     if (stage_init()) return 1;
     cudaStream_t s = as_stream(stream);
     XGB_CUDA(cudaEventRecord(g_stage_start, s));  // the lanes start after what `s` already holds
-    for (auto &l : g_lanes) XGB_CUDA(cudaStreamWaitEvent(l.stream, g_stage_start, 0));
+    const int kStageLanes = stage_lanes();
+    for (int i = 0; i < kStageLanes; ++i) XGB_CUDA(cudaStreamWaitEvent(g_lanes[i].stream, g_stage_start, 0));
     const size_t chunks = (bytes + kStageChunk - 1) / kStageChunk;
     char *dst = static_cast<char *>(dst_dev);
     const char *src = static_cast<const char *>(src_host);
@@ -392,7 +406,7 @@ int xgb_h2d_staged(void *dst_dev, const void *src_host, size_t bytes, xgb_handle
     });
     if (e != cudaSuccess) return fail(std::string("xgb_h2d_staged: ") + cudaGetErrorString(e));
     // the source has been read completely; `s` continues once every lane's last chunk has landed
-    for (auto &l : g_lanes) XGB_CUDA(cudaStreamWaitEvent(s, l.done, 0));
+    for (int i = 0; i < kStageLanes; ++i) XGB_CUDA(cudaStreamWaitEvent(s, g_lanes[i].done, 0));
     return 0;
 }
 
@@ -402,7 +416,8 @@ int xgb_d2h_staged(void *dst_host, const void *src_dev, size_t bytes, xgb_handle
     if (stage_init()) return 1;
     cudaStream_t s = as_stream(stream);
     XGB_CUDA(cudaEventRecord(g_stage_start, s));
-    for (auto &l : g_lanes) XGB_CUDA(cudaStreamWaitEvent(l.stream, g_stage_start, 0));
+    const int kStageLanes = stage_lanes();
+    for (int i = 0; i < kStageLanes; ++i) XGB_CUDA(cudaStreamWaitEvent(g_lanes[i].stream, g_stage_start, 0));
     const size_t chunks = (bytes + kStageChunk - 1) / kStageChunk;
     char *dst = static_cast<char *>(dst_host);
     const char *src = static_cast<const char *>(src_dev);
@@ -439,6 +454,72 @@ int xgb_d2h_staged(void *dst_host, const void *src_dev, size_t bytes, xgb_handle
     });
     if (e != cudaSuccess) return fail(std::string("xgb_d2h_staged: ") + cudaGetErrorString(e));
     return 0;  // synchronous: dst_host is complete
+}
+
+// ---- host half of the mask upload: int32 boundary -> packed bytes + chunk flags + histogram ----
+int xgb_mask_pack(const int32_t *src, size_t n, size_t n_padded, uint8_t *dst, uint8_t *flags,
+                  uint64_t *hist_256, int *bad, int threads) {
+    if (n_padded % 128 || n > n_padded) return fail("xgb_mask_pack: n_padded must be a multiple of 128 and >= n");
+    const size_t chunks = n_padded / 128;
+    if (threads <= 0) {
+        unsigned hw = std::thread::hardware_concurrency();
+        threads = hw ? (int)(hw > 16 ? 16 : hw) : 4;
+    }
+    if (chunks < (size_t(1) << 13)) threads = 1;          // under a million points a thread start costs more
+    if ((size_t)threads > chunks) threads = chunks ? (int)chunks : 1;
+    std::vector<std::vector<uint64_t>> hists(threads, std::vector<uint64_t>(256, 0));
+    std::atomic<int> any_bad{0};
+    auto work = [&](int t) {
+        uint64_t *h = hists[t].data();
+        const size_t c0 = chunks * t / threads, c1 = chunks * (t + 1) / threads;
+        for (size_t c = c0; c < c1; ++c) {
+            const size_t i0 = c * 128;
+            const size_t m = i0 >= n ? 0 : (n - i0 < 128 ? n - i0 : 128);
+            const int32_t *s = src + i0;
+            uint8_t *d = dst + i0;
+            int32_t acc = 0;
+            for (size_t k = 0; k < m; ++k) acc |= s[k];
+            if (acc == 0) {                               // the common chunk: interior, all zero
+                memset(d, 0, 128);
+                flags[c] = 0;
+                h[0] += m;
+                continue;
+            }
+            // pack (branch-free, vectorisable), then count only the non-zero bytes, eight at a time
+            alignas(8) uint8_t tmp[128];
+            for (size_t k = 0; k < m; ++k) {
+                const uint32_t v = (uint32_t)s[k];
+                tmp[k] = (uint8_t)(v > 254u ? 255u : v);
+            }
+            if (m < 128) memset(tmp + m, 0, 128 - m);
+            size_t nonzero = 0;
+            for (size_t w = 0; w < 16; ++w) {
+                uint64_t word;
+                memcpy(&word, tmp + 8 * w, 8);
+                if (!word) continue;
+                for (size_t k = 8 * w; k < 8 * w + 8; ++k)
+                    if (tmp[k]) { ++h[tmp[k]]; ++nonzero; }
+            }
+            if (h[255]) any_bad.store(1, std::memory_order_relaxed);
+            h[0] += m - nonzero;
+            memcpy(d, tmp, 128);
+            flags[c] = 1;
+        }
+    };
+    if (threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    for (int v = 0; v < 256; ++v) {
+        uint64_t sum = 0;
+        for (int t = 0; t < threads; ++t) sum += hists[t][v];
+        hist_256[v] = sum;
+    }
+    *bad = any_bad.load();
+    return 0;
 }
 
 // ---- streams / events ---------------------------------------------------------

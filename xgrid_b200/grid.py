@@ -16,7 +16,7 @@ Public surface and ring semantics follow the reference
   device -> host on demand and hand the level back to the host (the user may
   write through the returned array); the next kernel call re-uploads it;
 * the int32 ``boundary`` array is compiled on upload into a uint8 device mask,
-  per-128-point "any non-zero" flags and compacted index lists per mask value.
+  per-128-point "any non-zero" flags (packed on the host, runtime/maskpack.py) and compacted index lists.
 """
 from __future__ import annotations
 
@@ -44,7 +44,6 @@ def _flush() -> None:
 SLACK = 64          # elements of linear slack before / after the padded array
 CHUNK = 128         # points per mask flag (XGB_CHUNK in xgb_stencil.cuh)
 MASK_GHOST = 64     # bytes of "outside" (255) mask on both sides of the device mask
-SMALL_MASK = 1 << 20  # masks up to this many points are checked for "all zero" on the host
 ALIGN = 256
 
 
@@ -463,14 +462,18 @@ class Grid:
         self._mask_snapshot = None
         self._mask_hist = None
         self._mask_version += 1
-        flat = b.reshape(-1)
         nchunk = (self.size + CHUNK - 1) // CHUNK
-        # small grids: look on the host; big ones are classified by the histogram the device pass returns
-        # (a host scan of a 2^24-point int32 mask costs ~8 ms, the device pass reads it anyway)
-        if self.size <= SMALL_MASK and not flat.any() and not self.sharded:
-            self._mask_snapshot = np.zeros(self.shape, np.uint8)
-            self._mask_any = False      # all-zero class: kernels get null mask pointers
-            return
+        # pack on the host (several threads): one byte per point, chunk flags, histogram
+        from .runtime import maskpack
+        packed, flags, hist, bad = maskpack.pack(np.ascontiguousarray(b, np.int32), nchunk * CHUNK)
+        if bad:
+            self.logger.dead("boundary mask values must lie in [0, 254] on the B200 backend")
+        # host copy for change detection / index lists / the fused-pair check: the packed bytes
+        self._mask_snapshot = packed[:self.size].reshape(self.shape)
+        self._mask_hist = hist
+        self._mask_any = bool(self.sharded or int(hist[0]) != self.size)
+        if not self._mask_any:
+            return                      # all-zero class: kernels get null mask pointers, nothing is uploaded
         # device layout: [MASK_GHOST bytes of 255 | mask | zero padding to a whole chunk | MASK_GHOST x 255];
         # 255 = "outside the grid" (never matches a statement); on a sharded 1-D grid the ghost bytes
         # are replaced by the neighbours' edge masks
@@ -480,16 +483,7 @@ class Grid:
             self._flags_dev = rt.alloc(nchunk)
             rt.memset(self._mask_raw, 255, MASK_GHOST)
             rt.memset(self._mask_dev + nchunk * CHUNK, 255, MASK_GHOST)
-        from .runtime.devmask import compile_mask
-        hist, bad = compile_mask(rt, np.ascontiguousarray(b, np.int32), self._mask_dev, self._flags_dev,
-                                 nchunk * CHUNK)
-        if bad:
-            self.logger.dead("boundary mask values must lie in [0, 254] on the B200 backend")
-        # host copy for change detection / index lists / the fused-pair check: one byte per point
-        # (values were just validated), a quarter of the int32 array's traffic
-        self._mask_snapshot = b.astype(np.uint8)
-        self._mask_hist = hist
-        self._mask_any = bool(self.sharded or int(hist[0]) != self.size)
+        maskpack.upload(rt, packed, flags, self._mask_dev, self._flags_dev)
         if self.sharded and self.dimension == 1:
             from . import dist
             # trailing ghost sits right after the last real byte on the neighbour's side

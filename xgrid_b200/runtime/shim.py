@@ -49,6 +49,8 @@ SIGNATURES = {
     "xgb_d2d": [c_void_p, c_void_p, c_size_t, Handle],
     "xgb_h2d_staged": [c_void_p, c_void_p, c_size_t, Handle],
     "xgb_d2h_staged": [c_void_p, c_void_p, c_size_t, Handle],
+    "xgb_mask_pack": [POINTER(C.c_int32), c_size_t, c_size_t, POINTER(C.c_uint8), POINTER(C.c_uint8),
+                      POINTER(c_uint64), POINTER(c_int), c_int],
     "xgb_host_alloc": [c_size_t, POINTER(c_void_p)],
     "xgb_host_free": [c_void_p],
     "xgb_host_register": [c_void_p, c_size_t],
@@ -210,8 +212,9 @@ class Runtime:
     def d2h(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
         check(self.l.xgb_d2h(c_void_p(dst), c_void_p(src), nbytes, stream))
 
-    # pageable memory through the runtime's multi-threaded staging path (opt-in: XGB_STAGED_COPY=1)
-    STAGED = os.environ.get("XGB_STAGED_COPY", "0") == "1"
+    # pageable memory through the runtime's multi-threaded staging path (XGB_STAGED_COPY=0: the driver's
+    # single-threaded pageable cudaMemcpy instead)
+    STAGED = os.environ.get("XGB_STAGED_COPY", "1") == "1"
     STAGED_MIN = 8 << 20
 
     def h2d_staged(self, dst: int, src: int, nbytes: int, stream: int = 0) -> None:
