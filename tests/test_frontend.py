@@ -330,3 +330,41 @@ def test_device_code_is_the_gpu_validated_one(tmp_path):
     got = mod.hashes(str(tmp_path / "xg"))
     changed = sorted(k for k in set(want) | set(got) if want.get(k) != got.get(k))
     assert not changed, f"device code changed since its last GPU validation: {changed}"
+
+
+def test_external_operator_compiles_against_the_named_cuda_header(tmp_path, monkeypatch):
+    """`@xgrid.external(includes=[...])`: the reference emits an `extern` prototype and compiles the C file
+    in (generator.py:96-97,208-212); here the header holds a __device__ function and is handed to NVRTC."""
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "bump.h").write_text("__device__ __forceinline__ double bump(double x, double k) { return x * x + k; }\n")
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"))
+
+    @xgrid.external(includes=["bump.h"], typecheck_override=lambda args: args[0])
+    def bump(x: float, k: float) -> float:
+        ...
+
+    @xgrid.external(typecheck_override=lambda args: args[0])
+    def nowhere(x: float) -> float:
+        ...
+
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def apply(u: f1, k: float) -> None:
+        u[0] = bump(u[0], k) + u[-1]
+
+    @xgrid.kernel()
+    def broken(u: f1) -> None:
+        u[0] = nowhere(u[0])
+
+    @xgrid.kernel()
+    def scalar_use(k: float) -> float:
+        return bump(k, k)
+
+    assert '#include "bump.h"' in apply.src
+    for names, image in apply._program().images():            # NVRTC, sm_100a, with the user header
+        assert image[:4] == b"\x7fELF"
+    with pytest.raises(Exception, match="includes="):
+        broken.src
+    with pytest.raises(Exception, match="CUDA header"):
+        scalar_use(1.0)

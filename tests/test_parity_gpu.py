@@ -273,10 +273,11 @@ def test_multistep_matches_oracle(k64, kernel, n, steps):
     eq(u._data[1], h._data[1], "L1 after host write")
 
 
-@pytest.mark.parametrize("steps", [8, 11, 20, 62, 63])
+@pytest.mark.parametrize("steps", [8, 11, 20, 32, 33, 36, 62, 63])
 def test_multistep_tail_lengths(k64, steps):
-    """Runs shorter than T go through the tail variant (step count passed at run time); a second run
-    continues from the ring it left behind."""
+    """Runs shorter than T go through the run-time-step-count variants -- up to T/2 steps on the short
+    variant's half-size windows, longer ones on the tail variant; a second run continues from the ring
+    the first left behind.  Boundary points sit on both variants' window edges (W = 1984 / 3968)."""
     from xgrid_b200.lang.launch import STATS
     n = 40000
     ic, dx = W.ic_1d(n)
@@ -284,6 +285,10 @@ def test_multistep_tail_lengths(k64, steps):
     mask = np.zeros(n, np.int32)
     mask[0] = mask[-1] = 1
     mask[777] = 7
+    mask[1983] = 1
+    mask[1984] = 7
+    mask[3968] = 1
+    mask[3 * 3968 - 1] = 1
     u, h = make_grid(ic, mask), HostGrid((n,))
     h.now[...] = ic
     h.boundary[...] = mask

@@ -28,7 +28,7 @@ def test_1d_run_is_deferred_and_split_into_multistep_launches(rt):
     assert rt.launches == []                                  # nothing ran yet: 150 identical calls are queued
     xgrid.flush()
     names = rt.names()
-    assert names == (["xg_convection_1d_g0_multistep_v1"] * 2 + ["xg_convection_1d_g0_multistep_tail_v1"]
+    assert names == (["xg_convection_1d_g0_multistep_v1"] * 2 + ["xg_convection_1d_g0_multistep_short_v1"]
                      + ["xg_convection_1d_g0_dense_v4"] * 2), names
     full, tail = rt.launches[0][3], rt.launches[2][3]
     assert tail["opt0"] == 20 and full["n0"] == n
@@ -46,7 +46,7 @@ def test_changing_a_scalar_or_reading_now_flushes(rt):
     for _ in range(10):
         k(u, 1.0, 0.5, 1.0)
     k(u, 1.0, 0.25, 1.0)                                      # other arguments: the queued run executes first
-    assert rt.names() == ["xg_convection_1d_g0_multistep_tail_v1", "xg_convection_1d_g0_dense_v4",
+    assert rt.names() == ["xg_convection_1d_g0_multistep_short_v1", "xg_convection_1d_g0_dense_v4",
                           "xg_convection_1d_g0_dense_v4"]
     before = len(rt.launches)
     _ = u.now                                                 # host read: flush the one pending call, then D2H
@@ -209,7 +209,7 @@ def test_sharded_1d_run_gets_its_halo_layout_with_the_first_deferred_call(monkey
     assert [c[0] for c in rt.copies] == ["h2d"] * 3 and rt.real_frees == 0
     assert rt.real_allocs - allocs <= 4                                     # level 0/1 + mask + flags, no re-layout
     names = rt.names()
-    assert names[0].endswith("multistep_tail_v1") and rt.launches[0][3]["opt0"] == 20
+    assert names[0].endswith("multistep_short_v1") and rt.launches[0][3]["opt0"] == 20
     assert [e[2] for e in tr.log if e[0] == "exchange"] == [H, H]           # both ring levels, H deep
     # second run of 21: tail launch of 20 + one single step; the single step's depth-1 exchange must not
     # pass for fresh when the next multi-step launch asks for H
@@ -427,3 +427,53 @@ def test_writes_through_a_retained_now_array_reach_the_device(rt):
     k(u, 0.01, 0.1, 1.0)
     assert ("h2d", lv.dev, 4096 * 8) in rt.copies[copies:]    # uploaded again before the sweep
     assert u.now is u.now
+
+
+def test_short_runs_use_the_half_window_variant(rt):
+    """A remainder of at most T/2 = 32 steps runs on the short variant (256 threads, half the window, five
+    CTAs per SM); longer remainders keep the tail variant; both read their step count from the launch."""
+    k = W.make_kernels()["diffusion_1d"]
+    n = 1 << 17
+    u = xgrid.Grid((n,), float)
+    u.boundary[0] = u.boundary[-1] = 1
+    for count, want, steps in ((20, "multistep_short_v1", 20), (32, "multistep_short_v1", 32),
+                               (36, "multistep_tail_v1", 36), (63, "multistep_tail_v1", 60)):
+        before = len(rt.launches)
+        for _ in range(count):
+            k(u, 0.01, 0.1, 1.0)
+        xgrid.flush()
+        first = rt.launches[before]
+        assert first[0].endswith(want) and first[3]["opt0"] == steps, (count, first[0], first[3]["opt0"])
+        cfg = k._program().groups[0].multistep_short if "short" in want else k._program().groups[0].multistep
+        assert first[2] == (cfg["threads"], 1, 1) and first[1][0] == -(-n // cfg["W"])
+        assert len(rt.launches) - before == 1 + (count - steps)
+
+
+def test_callee_operators_with_grids_run_their_own_sweeps_in_program_order(rt, tmp_path):
+    """generator.py:208-212,418-419: a called operator's statements run in place of the call, on the caller's
+    buffers, without a tick of their own; the callee's deepest time level sets the caller's ring depth."""
+    import importlib.util
+    import os
+    import xgrid
+    spec = importlib.util.spec_from_file_location(
+        "callee_prog_fake", os.path.join(os.path.dirname(__file__), "programs", "callee_prog.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    u, v = xgrid.Grid((24, 24), float), xgrid.Grid((24, 24), float)
+    u.boundary[0, :] = 1
+    v.boundary[0, :] = 1
+    mod.outer(u, v, 0.4)
+    assert mod.outer.depth == 3 and len(u._ring) == len(v._ring) == 3
+    names = [n.split("_g")[0] for n in rt.names()]
+    # relax(u) | v = u + 1 (+ its boundary statement, fused) | relax(v) | smooth: 3 x (Jacobi sweep + Neumann copy)
+    assert names == ["xg_relax", "xg_outer", "xg_relax"] + ["xg_smooth"] * 6, rt.names()
+    first, second = rt.launches[0][3], rt.launches[2][3]
+    assert first["s0"] in {lv.dev for lv in u._ring} | {u._scratch.dev}    # (smooth swapped level 0 / scratch)
+    assert second["s0"] in {lv.dev for lv in v._ring}          # the same callee, bound to the other grid
+    # no extra tick: one rotation per call of the OUTER kernel only
+    before = [lv.dev for lv in v._ring]
+    mod.outer(u, v, 0.4)
+    assert [lv.dev for lv in v._ring] == before[-1:] + before[:-1]
+    for _ in range(30):                                         # (the 4 buffers of u permute with a long period)
+        mod.outer(u, v, 0.4)
+    assert rt.graphs                                            # calls with callees are recorded and replayed too

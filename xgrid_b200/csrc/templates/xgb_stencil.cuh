@@ -287,6 +287,13 @@ XGB_DEV int ld_flag(const uint8_t *mask, const uint8_t *flags, int64_t base) {
     if (flags == nullptr) return 1;
     return flags[base >> XGB_CHUNK_SHIFT];
 }
+// Warp-uniform form for the pipeline kernels: "does any point of [lo, hi] (one warp's vector span of one row)
+// lie in a chunk that holds a boundary point?"  A span is shorter than a chunk, so it touches at most two.
+XGB_DEV int ld_flag_span(const uint8_t *mask, const uint8_t *flags, int64_t lo, int64_t hi) {
+    if (mask == nullptr) return 0;
+    if (flags == nullptr) return 1;
+    return __ldg(flags + (lo >> XGB_CHUNK_SHIFT)) | __ldg(flags + (hi >> XGB_CHUNK_SHIFT));
+}
 template <int V>
 XGB_DEV void ld_mask_flagged(const uint8_t *mask, int flag, int64_t base, int (&m)[V]) {
 #pragma unroll

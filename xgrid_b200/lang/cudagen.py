@@ -28,6 +28,7 @@ VARIANT_MARCH = "march"
 VARIANT_TILED = "tiled"
 VARIANT_MULTISTEP = "multistep"
 VARIANT_MULTISTEP_TAIL = "multistep_tail"
+VARIANT_MULTISTEP_SHORT = "multistep_short"     # run-time step count <= T/2 on half-size windows (short runs)
 VARIANT_TILED2 = "tiled2"
 MARCH_ROWS = {2: 16, 3: 8}      # unroll depth of the marching loop (axis-0 points per trip)
 import os as _os
@@ -79,6 +80,7 @@ class Group:
     march: bool = False                           # has axis-0 marching variants
     tiled: dict | None = None                     # geometry of the async shared-memory pipeline variant
     multistep: dict | None = None                 # temporal-blocking variant (1-D, whole-kernel groups)
+    multistep_short: dict | None = None           # its short-run sibling (half the halo, half the window)
     tiled2: dict | None = None                    # two time steps per pass, 2-D (time-skewed tiled pipeline)
 
     def slot(self, grid: str, level) -> Slot:
@@ -200,7 +202,16 @@ class ModuleBuilder:
         self.structs: dict[str, str] = {}
         self.functions: dict[str, str] = {}
         self.kernels: list[str] = []
+        self.includes: list[str] = []          # user headers (`includes=` of the kernel and of every operator it calls)
         self._shape_ref = None
+
+    def include(self, names) -> None:
+        for n in names:
+            if n not in self.includes:
+                self.includes.append(n)
+
+    def _preamble(self) -> list:
+        return ['#include "xgb_stencil.cuh"\n', *[f'#include "{n}"\n' for n in self.includes]]
 
     # ---- types
     def ctype(self, t) -> str:
@@ -225,8 +236,15 @@ class ModuleBuilder:
 
     # ---- callee operators become __device__ functions (generator.py:208-212,418-419)
     def device_function(self, op) -> str:
+        self.include(op.includes)
         if op.mode == "external":
-            raise CodegenError(f"external operator '{op.name}' cannot be called from device code")
+            # the reference emits an `extern` prototype and leaves the definition to the C files named in
+            # `includes=` (generator.py:208-212); here the definition is a `__device__` function in a CUDA
+            # header named the same way -- the call is emitted by name and the header must declare it
+            if not op.includes:
+                raise CodegenError(f"external operator '{op.name}' needs `includes=[...]` naming the CUDA header "
+                                   "that defines it as a __device__ function")
+            return op.name
         cname = op.name.replace(".", "_")
         if cname in self.functions:
             return cname
@@ -288,7 +306,7 @@ class ModuleBuilder:
 
     # ---- final text
     def source(self) -> str:
-        parts = ['#include "xgb_stencil.cuh"\n']
+        parts = self._preamble()
         parts.extend(self.structs.values())
         parts.extend(self.functions.values())
         parts.extend(self.kernels)
@@ -300,7 +318,7 @@ class ModuleBuilder:
         functions, parameter structs, inline-block prelude) in their original order and a share of
         the kernels, balanced by text length -- kernels only depend on declarations, never on each
         other."""
-        shared = ['#include "xgb_stencil.cuh"\n', *self.structs.values(), *self.functions.values()]
+        shared = [*self._preamble(), *self.structs.values(), *self.functions.values()]
         kernels = []
         for text in self.kernels:
             names = _KERNEL_NAME.findall(text)
@@ -454,6 +472,9 @@ def emit_group(g: Group, module: ModuleBuilder, scope: dict, grid_ndims: dict) -
             if g.multistep is not None:
                 module.kernels.append(_emit_multistep(g, module, g.multistep))
                 module.kernels.append(_emit_multistep(g, module, g.multistep, tail=True))
+                g.multistep_short = multistep_config(g, short=True)
+                if g.multistep_short is not None:
+                    module.kernels.append(_emit_multistep(g, module, g.multistep_short, tail=True, short=True))
             g.tiled2 = tiled2_config(g)
             if g.tiled2 is not None:
                 module.kernels.append((_emit_tiled2_3d if g.ndim == 3 else _emit_tiled2)(g, module, g.tiled2))
@@ -853,7 +874,8 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
         L.append("    const int64_t S0 = p.cols;")
     L.append("    if (i0 >= p.r_hi) return;")
     L.append("    const int64_t iend = (i0 + p.chunk0 < p.r_hi) ? (i0 + p.chunk0) : p.r_hi;")
-    L.append("    const int planes = (int)(iend - i0) + DSPAN;          // input planes this CTA streams")
+    L.append("    const int nout = (int)(iend - i0);                    // output planes of this CTA")
+    L.append("    const int planes = nout + DSPAN;                      // input planes this CTA streams")
     L.append("    if (threadIdx.x == 0) {")
     L.append("        for (int s = 0; s < NS; ++s) { xgb::pipe::mbar_init(&full[s], 1); xgb::pipe::mbar_init(&empty[s], NCW); }")
     L.append("        xgb::pipe::fence_barrier_init();")
@@ -893,19 +915,32 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
     L.append("        act[sv] = (col < p.cols)" + (" && (j < p.n1);" if nd == 3 else ";"))
     L.append("        base[sv] = act[sv] ? (i0 * S0 + " + ("j * p.n2 + " if nd == 3 else "") + "col) : (i0 * S0);")
     L.append("    }")
+    # chunk flags ("any boundary point near this warp's span of the row?"), fetched 32 planes at a time: lane l
+    # asks for plane it0 + l, the loop broadcasts one lane's answer per plane with a shuffle.  The round trip
+    # to global memory is paid once per 32 planes (the first one while the pipeline fills) instead of once per
+    # plane inside the dependent chain of every output vector (ncu, round 1: 41 % of all stall samples).
     for m in g.masks:
-        L.append(f"    int fl_{m}[NSV];")
-        L.append(f"#pragma unroll\n    for (int sv = 0; sv < NSV; ++sv) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv]);")
+        L.append(f"    int fb_{m}[NSV];")
     L.append("    const T *srow = stages + (int64_t)(ty + HJ) * WP + HK;   // this warp's row inside a plane")
     L.append("    int fs = 0, fph = 0;                                  // stage / parity of the newest plane")
-    L.append("    for (int t = 0; t < DSPAN; ++t) { xgb::pipe::mbar_wait(&full[fs], fph); if (++fs == NS) { fs = 0; fph ^= 1; } }")
     L.append("    int ps = 0;                                           // stage of plane o + DMIN")
-    L.append("    const int nout = (int)(iend - i0);")
     L.append("    for (int it = 0; it < nout; ++it) {")
+    if g.masks:
+        L.append("        if ((it & 31) == 0) {                             // (warp-uniform) flags of the next 32 planes")
+        L.append("#pragma unroll")
+        L.append("            for (int sv = 0; sv < NSV; ++sv) {")
+        L.append("                const int64_t col0 = c0 + (int64_t)(wx * NSV + sv) * (32 * V);")
+        L.append("                const bool wact = (col0 < p.cols)" + (" && (j < p.n1)" if nd == 3 else "") + " && (it + lane < nout);")
+        L.append("                const int64_t row0 = (i0 + it + lane) * S0" + (" + j * p.n2;" if nd == 3 else ";"))
+        L.append("                const int64_t col1 = (col0 + 32 * V < p.cols) ? (col0 + 32 * V) : p.cols;")
+        for m in g.masks:
+            L.append(f"                fb_{m}[sv] = wact ? xgb::ld_flag_span(p.m_{m}, p.f_{m}, row0 + col0, row0 + col1 - 1) : 0;")
+        L.append("            }")
+        L.append("        }")
+    L.append("        if (it == 0) for (int t = 0; t < DSPAN; ++t) { xgb::pipe::mbar_wait(&full[fs], fph); if (++fs == NS) { fs = 0; fph ^= 1; } }")
     for m in g.masks:
         L.append(f"        int fc_{m}[NSV];")
-        L.append(f"#pragma unroll\n        for (int sv = 0; sv < NSV; ++sv) {{ fc_{m}[sv] = fl_{m}[sv]; "
-                 f"if (it + 1 < nout) fl_{m}[sv] = xgb::ld_flag(p.m_{m}, p.f_{m}, base[sv] + S0); }}")
+        L.append(f"#pragma unroll\n        for (int sv = 0; sv < NSV; ++sv) fc_{m}[sv] = __shfl_sync(0xffffffffu, fb_{m}[sv], it & 31);")
     L.append("        xgb::pipe::mbar_wait(&full[fs], fph);")
     L.append("        if (++fs == NS) { fs = 0; fph ^= 1; }")
     # stage base of every input plane this output plane reads (once per plane, not per tap)
@@ -983,9 +1018,12 @@ MULTISTEP_S = int(_os.environ.get("XGB_MS_S", "4"))      # register sub-steps pe
 MULTISTEP_P = int(_os.environ.get("XGB_MS_P", "8"))      # points per thread in the register path
 
 
-def multistep_config(g: Group):
+def multistep_config(g: Group, short: bool = False):
     """1-D groups that read only the previous level of the ONE grid they update can run T
-    time steps per launch from shared memory."""
+    time steps per launch from shared memory.  ``short``: the variant for
+    runs of at most T/2 steps -- half the halo and half the window (256 threads, ~43 KB of shared memory, so
+    five CTAs per SM instead of two): a launch's fixed cost is its load and store phases, which only
+    overlap ACROSS resident CTAs."""
     if g.ndim != 1 or g.implicit or g.sparse:
         return None
     if not any(st.sweep.mask == 0 for st in g.stmts):
@@ -1005,6 +1043,8 @@ def multistep_config(g: Group):
     T = MULTISTEP_T
     while T * h > 64:                 # halo must stay inside the level's zero slack
         T //= 2
+    if short:
+        T //= 2
     S = MULTISTEP_S                   # time steps advanced in registers per shared-memory round trip
     T -= T % (2 * S) if T >= 2 * S else T % 2
     if T < 4:
@@ -1013,7 +1053,7 @@ def multistep_config(g: Group):
         S = 2
     if (S * h) % (16 // elem.width_bytes):
         return None                   # register windows must start on a 16-byte boundary
-    NT, P = 512, MULTISTEP_P
+    NT, P = (256 if short else 512), MULTISTEP_P
     H = T * h
     L = NT * P                        # window = one P-point body per thread
     if L <= 4 * H:
@@ -1028,7 +1068,7 @@ def multistep_config(g: Group):
             "smem": 2 * (swlen + 2 * marg) * elem.width_bytes + L + 64}
 
 
-def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False) -> str:
+def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False, short: bool = False) -> str:
     """T steps per launch (``tail``: the same kernel with the step count read from ``p.opt0`` --
     a multiple of S below T -- for the remainder of a deferred run; the window keeps its T*h halo).  Two shared-memory buffers start as copies of the two ring levels
     (now / previous) of an L = W+2H window; every step writes the *older* buffer where a
@@ -1071,7 +1111,7 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False
             reg_lines.append(f"                x{s_}[i] = x{s_ - 1}[i + {h}];")
         reg_lines.append("            }")
 
-    name = kernel_name(g, VARIANT_MULTISTEP_TAIL if tail else VARIANT_MULTISTEP, 1)
+    name = kernel_name(g, VARIANT_MULTISTEP_SHORT if short else VARIANT_MULTISTEP_TAIL if tail else VARIANT_MULTISTEP, 1)
     nsteps = "(int)p.opt0" if tail else "T"
     L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
     L.append(f"    constexpr int T = {c['T']}, S = {S}, P = {P}, PSH = {psh}, HS = {h}, H = {c['H']}, W = {c['W']}, L = {c['L']}, "
@@ -1098,14 +1138,30 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False
     L.append("        else { for (int v = 0; v < V; ++v) { a[v] = E(0); b[v] = E(0); } }")
     L.append("        xgb::st_vec<E, V>(b0 + XSW(q), a); xgb::st_vec<E, V>(b1 + XSW(q), b);")
     L.append("    }")
-    L.append("    int any = 0;")
-    L.append("    for (int q = threadIdx.x; q < L; q += NT) {")
-    L.append("        const int64_t gi = g0 + q;")
-    L.append("        int m = 255;                                  // outside the grid: never updated")
-    L.append(f"        if ((gi >= 0 || p.open_lo) && (gi < p.n0 || p.open_hi)) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
-    L.append("        sm[q] = (uint8_t)m; any |= m;")
+    L.append("    // A window that lies inside the grid and whose chunk flags are all clear has no boundary point: it")
+    L.append("    // takes the register path without fetching a mask byte (L/128 + 1 flag bytes instead of L mask bytes).")
+    L.append("    int any = 1;")
+    L.append("    if (g0 >= 0 && g0 + L <= p.n0) {")
+    L.append("        any = 0;")
+    L.append(f"        if (p.m_{gname} != nullptr) {{")
+    L.append(f"            if (p.f_{gname} == nullptr) any = 1;")
+    L.append(f"            else if ((int)threadIdx.x <= (L >> XGB_CHUNK_SHIFT)) {{")
+    L.append(f"                const int64_t ch = (g0 >> XGB_CHUNK_SHIFT) + threadIdx.x;")
+    L.append(f"                if ((ch << XGB_CHUNK_SHIFT) < g0 + L) any = p.f_{gname}[ch];")
+    L.append("            }")
+    L.append("        }")
     L.append("    }")
-    L.append("    const int masked = __syncthreads_or(any);")
+    L.append("    int masked = __syncthreads_or(any);")
+    L.append("    if (masked) {")
+    L.append("        any = 0;")
+    L.append("        for (int q = threadIdx.x; q < L; q += NT) {")
+    L.append("            const int64_t gi = g0 + q;")
+    L.append("            int m = 255;                              // outside the grid: never updated")
+    L.append(f"            if ((gi >= 0 || p.open_lo) && (gi < p.n0 || p.open_hi)) m = (p.m_{gname} != nullptr) ? p.m_{gname}[gi] : 0;")
+    L.append("            sm[q] = (uint8_t)m; any |= m;")
+    L.append("        }")
+    L.append("        masked = __syncthreads_or(any);")
+    L.append("    }")
     L.append("    if (!masked) {")
     L.append("        // register path: S steps per round; b0 always receives the newest level (S is even)")
     L.append("        const int first = threadIdx.x * P;")

@@ -44,7 +44,7 @@ class Operator:
             from .frontend import Parser
             parsed = Parser(self.func, self.name, self.mode, self.self_type)
             self._ir = parsed.result
-            self.includes.extend(parsed.includes)
+            self.includes.extend(h for h in parsed.includes if h not in self.includes)
         return self._ir
 
     @property

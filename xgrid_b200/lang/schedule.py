@@ -151,9 +151,10 @@ def coerce(t, value):
 class HostEval:
     """Evaluates scalar IR with C semantics (the host half of a kernel)."""
 
-    def __init__(self, env: dict, grids: dict) -> None:
+    def __init__(self, env: dict, grids: dict, launcher=None) -> None:
         self.env = env          # name -> numpy scalar | dataclass | ctypes pointer target
         self.grids = grids
+        self.launcher = launcher    # the calling kernel's launcher (None: scalar-only context)
 
     def __call__(self, e):
         return getattr(self, "v_" + type(e).__name__)(e)
@@ -240,11 +241,13 @@ class HostEval:
         raise Exception(f"grid access to '{e.variable.name}' outside a stencil statement")
 
     def v_Call(self, e):
-        args = [self(a) for a in e.arguments]
+        # a grid argument is the Grid object itself (the reference passes its struct by value: same buffers)
+        args = [self.grids[a.variable.name] if isinstance(a.type, GridT) and isinstance(a, ir.Identifier) else self(a)
+                for a in e.arguments]
         if isinstance(e.operator, ir.Constructor):
             st = e.operator.type
             return st.dataclass(*[_to_py(a) for a in args])
-        return call_scalar_operator(e.operator, args, self.grids)
+        return call_operator(e.operator, args, self.launcher)
 
 
 def _to_py(v):
@@ -264,24 +267,53 @@ def _store_ptr(p, v):
         p.value = _to_py(v)
 
 
-def call_scalar_operator(op, args, grids):
-    """Interpret a called ``@function`` / ``@kernel`` operator whose body is
-    scalar-only (the reference compiles it into the same TU,
-    generator.py:208-212)."""
+def call_operator(op, args, caller_launcher=None):
+    """A call of another ``@kernel`` / ``@function`` operator from a kernel's host-side code.  The
+    reference emits the callee into the same translation unit and calls it like any C function
+    (xgrid/lang/generator.py:208-212,418-419): no tick, no ring resize -- the callee's statements simply
+    run, in order, on the caller's buffers.  Here a scalar-only callee is interpreted on the host; a callee
+    with grid parameters runs ITS program's plan (its own generated sweep kernels, fused groups, solver
+    pairs) through a launcher bound to the caller's Grid objects, on the same stream."""
     if op.mode == "external":
-        raise Exception(f"external operator '{op.name}' has no host implementation")
+        raise Exception(f"external operator '{op.name}' is defined by a CUDA header (includes=[...]) and can only "
+                        "be called from stencil statements, not from a kernel's scalar code")
     d = op.ir
-    env = {}
+    env, grids = {}, {}
     for (n, t), v in zip(d.signature.arguments, args):
-        env[n] = coerce(t, v) if isinstance(t, Structure) else v      # by-value struct parameters
-    runner = _Interpreter(d, env, grids, launcher=None)
-    return runner.run(build_plan(d.body, [], None))
+        if isinstance(t, GridT):
+            grids[n] = v
+        else:
+            env[n] = coerce(t, v) if isinstance(t, Structure) else v  # by-value struct parameters
+    if not grids:
+        return _Interpreter(d, env, {}, launcher=None).run(build_plan(d.body, [], None))
+    if caller_launcher is None:
+        raise Exception(f"operator '{op.name}' takes grids and can only be called from a kernel")
+    if _Launcher is None:
+        _late_imports()
+    prog = op._program()
+    return _Interpreter(prog.ir, env, grids, _Launcher(prog, grids), prog.pairs).run(prog.plan)
+
+
+def grid_callees(body) -> list:
+    """Operators with grid parameters called (directly) from these statements."""
+    out = []
+    for st in ir.walk_stmts(body):
+        for root in (getattr(st, "value", None), getattr(st, "condition", None)):
+            if root is None or isinstance(root, (list, str)):
+                continue
+            for e in ir.walk_expr(root):
+                if isinstance(e, ir.Call) and not isinstance(e.operator, ir.Constructor) \
+                        and e.operator.mode != "external" \
+                        and any(isinstance(t, GridT) for _, t in e.operator.signature.arguments) \
+                        and e.operator not in out:
+                    out.append(e.operator)
+    return out
 
 
 class _Interpreter:
     def __init__(self, definition, env, grids, launcher, pairs=None) -> None:
         self.d, self.env, self.grids, self.launcher = definition, env, grids, launcher
-        self.ev = HostEval(env, grids)
+        self.ev = HostEval(env, grids, launcher if callable(getattr(launcher, "_params", None)) else None)
         self.pairs = pairs or {}        # id(ir.For) -> jacobi2.Pair (two iterations per pass)
 
     def run(self, plan):
@@ -295,7 +327,7 @@ class _Interpreter:
         for node in plan:
             if isinstance(node, GroupNode):
                 if self.launcher is None:
-                    raise Exception("stencil statements inside called operators are not supported")
+                    raise Exception("stencil statements need a kernel context (grids bound to a launcher)")
                 self.launcher(node.group, self.env)
                 continue
             kind = node[0]
@@ -468,6 +500,9 @@ class Program:
         Program._serial += 1
         tag = "".join(ch if ch.isalnum() else "_" for ch in op.name)
         self.module_builder = cudagen.ModuleBuilder(self.config.overstep, self.config.comment)
+        self.module_builder.include(op.includes)
+        # operators with grid parameters called from this kernel run their own programs on our buffers
+        self.callees = grid_callees(self.ir.body)
         scope_types = {n: v.type for n, v in self.ir.scope.items()}
         for g in self.groups:
             g.name = f"xg_{tag}_g{g.gid}"
@@ -500,7 +535,7 @@ class Program:
         self.batchable = False
         self._grid_pos = -1
         if (len(self.groups) == 1 and self.groups[0].multistep is not None and self.depth == 2
-                and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
+                and not self.callees and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
                 and isinstance(self.ir.signature.return_type, Void)
                 and isinstance(self.plan[-1], GroupNode)
                 and all(isinstance(n, tuple) and n[0] == "stmt" and isinstance(n[1], ir.Assignment)
@@ -512,7 +547,7 @@ class Program:
         # two-steps-per-pass variant for 2-D kernels (same program shape, one 2-D group)
         self.batchable2 = False
         if (len(self.groups) == 1 and self.groups[0].tiled2 is not None and self.depth == 2
-                and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
+                and not self.callees and len(self.grid_args) == 1 and op.tick and self.config.overstep == "none"
                 and isinstance(self.ir.signature.return_type, Void)
                 and isinstance(self.plan[-1], GroupNode)
                 and all(isinstance(n, tuple) and n[0] == "stmt" and isinstance(n[1], ir.Assignment)
@@ -529,6 +564,21 @@ class Program:
         self.cacheable = not any(
             isinstance(st, ir.Assignment) and isinstance(st.terminal, ir.Identifier)
             and isinstance(st.terminal.variable.type, Pointer) for st in ir.walk_stmts(self.ir.body))
+
+    def halo0(self, _seen=None) -> int:
+        """Largest axis-0 reach of any sweep this call can launch, callee programs included."""
+        seen = _seen if _seen is not None else set()
+        seen.add(id(self.op))
+        h = max([1] + [g.halo0 for g in self.groups])
+        for op in self.callees:
+            if id(op) not in seen:
+                h = max(h, op._program().halo0(seen))
+        return h
+
+    def replayable(self, _seen=None) -> bool:
+        seen = _seen if _seen is not None else set()
+        seen.add(id(self.op))
+        return self.cacheable and all(id(op) in seen or op._program().replayable(seen) for op in self.callees)
 
     def _match_pairs(self, plan: list) -> None:
         for node in plan:
@@ -555,7 +605,8 @@ class Program:
     def _compile_cached(self, source: str, label: str) -> bytes:
         """One NVRTC compilation through the on-disk cache (sha256 of source + flags + template headers)."""
         from ..runtime import shim
-        headers = template_headers()
+        headers = dict(template_headers())
+        headers.update(self._user_headers())
         flags = self.config.nvrtc_flags
         key = hashlib.sha256("\0".join([source, *flags, *headers.values()]).encode()).hexdigest()[:32]
         root = os.path.join(".", self.config.cacheroot)
@@ -577,6 +628,30 @@ class Program:
         os.replace(tmp, cubin)
         self.logger.info(f"jit compiled '{cu}' to '{cubin}'")
         return image
+
+    def _user_headers(self) -> dict:
+        """CUDA headers named by `includes=` / `import a.b` (reference: `#include "a/b.h"` resolved by gcc
+        relative to the working directory, generator.py:96-97): read here and handed to NVRTC by name.
+        Looked up in the working directory, then next to the kernel's source file."""
+        out = {}
+        if not self.module_builder.includes:
+            return out
+        roots = ["."]
+        try:
+            import inspect
+            roots.append(os.path.dirname(os.path.abspath(inspect.getsourcefile(self.op.func))))
+        except (TypeError, OSError):
+            pass
+        for name in self.module_builder.includes:
+            for root in roots:
+                path = os.path.join(root, name)
+                if os.path.isfile(path):
+                    with open(path) as f:
+                        out[name] = f.read()
+                    break
+            else:
+                self.logger.dead(f"header '{name}' (includes= / import) was not found in {roots}")
+        return out
 
     def image(self) -> bytes:
         """The whole translation unit as ONE sm_100a cubin (tools, tests, the build check)."""
@@ -728,6 +803,8 @@ class Program:
         if self.batchable:
             wanted += [(cudagen.kernel_name(g, v, 1), g.multistep["smem"])
                        for v in (cudagen.VARIANT_MULTISTEP, cudagen.VARIANT_MULTISTEP_TAIL)]
+            if g.multistep_short is not None:
+                wanted.append((cudagen.kernel_name(g, cudagen.VARIANT_MULTISTEP_SHORT, 1), g.multistep_short["smem"]))
         else:
             wanted.append((cudagen.kernel_name(g, cudagen.VARIANT_TILED2, g.tiled2["V"]), g.tiled2["smem"]))
         if JIT_MODE == "lazy":
@@ -769,14 +846,14 @@ class Program:
         for (name, t), a in zip(sig, args):
             if isinstance(t, GridT):
                 a._op_invoke(self.depth, self.op.tick)   # once per argument, like the reference
-        ghost = max([1] + [g.halo0 for g in self.groups])
+        ghost = self.halo0()
         for g in grids.values():
             g._prepare_device(ghost)
 
         Launcher = _Launcher
         sharded = any(g.sharded for g in grids.values())
-        key = self._graph_key(env, grids) if (self.config.graphs and self.cacheable and self.groups
-                                              and not sharded) else None
+        key = self._graph_key(env, grids) if (self.config.graphs and self.replayable()
+                                              and (self.groups or self.callees) and not sharded) else None
         hit = self._graphs.get(key) if key is not None else None
         if hit is not None:
             # steady state: replay the recorded launches, then apply the recorded buffer permutation
@@ -787,7 +864,7 @@ class Program:
 
         launcher = Launcher(self, grids)
         record = key is not None and key in self._seen
-        rt = self._runtime() if self.groups else None
+        rt = self._runtime() if (self.groups or self.callees) else None
         if record:
             rt.graph_begin()
         try:
@@ -923,14 +1000,18 @@ class Program:
             marshal = Launcher(self, grids)
             for name, t in g.scalars.items():
                 setattr(P, f"u_{name}", marshal._scalar_value(t, env[name]))
-            blocks = (grid.shape[0] + cfg["W"] - 1) // cfg["W"]
+            short = g.multistep_short
             if grid.sharded:
                 from .. import dist
                 topo = dist.topology()
                 P.open_lo, P.open_hi = int(topo.lo_rank >= 0), int(topo.hi_rank >= 0)
             for steps in launches:
-                variant = cudagen.VARIANT_MULTISTEP if steps == T else cudagen.VARIANT_MULTISTEP_TAIL
-                fn = self.function(cudagen.kernel_name(g, variant, 1), cfg["smem"])
+                # a remainder of at most T/2 steps runs on the short variant's half-size windows
+                mc = short if (steps != T and short is not None and steps <= short["T"]) else cfg
+                variant = (cudagen.VARIANT_MULTISTEP if steps == T else
+                           cudagen.VARIANT_MULTISTEP_SHORT if mc is short else cudagen.VARIANT_MULTISTEP_TAIL)
+                fn = self.function(cudagen.kernel_name(g, variant, 1), mc["smem"])
+                blocks = (grid.shape[0] + mc["W"] - 1) // mc["W"]
                 x0, x1 = grid._ring[0], grid._ring[1]
                 if grid.sharded:
                     stale = [(grid, lv, cfg["H"]) for lv in (x0, x1) if lv.halo_rows < cfg["H"]]
@@ -939,7 +1020,7 @@ class Program:
                 c, d = grid._spare_levels(2)
                 P.aux0, P.aux1, P.aux2, P.aux3 = x0.dev, x1.dev, c.dev, d.dev
                 P.opt0 = steps
-                rt.launch(fn, (blocks, 1, 1), (cfg["threads"], 1, 1), P, smem=cfg["smem"])
+                rt.launch(fn, (blocks, 1, 1), (mc["threads"], 1, 1), P, smem=mc["smem"])
                 STATS["multistep"] = STATS.get("multistep", 0) + 1
                 grid._ring, grid._spares = [c, d], [x0, x1]
                 c.where = d.where = "device"
