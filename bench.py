@@ -160,9 +160,7 @@ def build_inputs(name: str, shape, seed: int = 0, ic_mode: str = "default"):
             return [(ic, mask)], (1.0, 0.5 * dx, dx, dx)
         return [(ic, W.shell_mask(shape))], (0.2,)
     if name == "heat3d":
-        rng = np.random.default_rng(seed)
-        ic = rng.random(shape)
-        return [(ic, W.shell_mask(shape))], (0.1,)
+        return [(_fill_random(seed), _fill_shell(shape, 0, shape[0]))], (0.1,)
     if name == "cavity":
         n0, n1 = shape
         mb, mp, mu, mv = W.cavity_masks(n0, n1)
@@ -183,14 +181,40 @@ def build_inputs(name: str, shape, seed: int = 0, ic_mode: str = "default"):
     raise SystemExit(f"unknown workload {name}")
 
 
+def _fill_random(seed: int):
+    """In-place initial condition for the big 3-D slab (8 GiB per level): U[0,1) written straight into the
+    grid's own host array -- no second copy of the level in host memory."""
+    def fill(out: np.ndarray) -> None:
+        np.random.default_rng(seed).random(out=out.reshape(-1))
+    return fill
+
+
+def _fill_shell(global_shape, lo: int, hi: int):
+    """In-place rows [lo, hi) of examples.workloads.shell_mask(global_shape)."""
+    def fill(out: np.ndarray) -> None:
+        out[...] = 1
+        inner = tuple(slice(1, -1) for _ in global_shape[1:])
+        a, b = max(lo, 1) - lo, min(hi, global_shape[0] - 1) - lo
+        if b > a:
+            out[(slice(a, b),) + inner] = 0
+    return fill
+
+
+def _put(dst, src) -> None:
+    """Write an input (array, or in-place filler) into a grid's host array."""
+    if callable(src):
+        src(np.asarray(dst))
+    else:
+        dst[...] = src
+
+
 def build_slab_inputs(name: str, shape, rank: int, world: int):
     """Weak scaling: every rank owns a `shape` slab of the (world*shape[0], ...) global grid."""
     from examples import workloads as W
     gshape = (shape[0] * world,) + tuple(shape[1:])
     lo, hi = rank * shape[0], (rank + 1) * shape[0]
     if name == "heat3d":
-        rng = np.random.default_rng(rank)
-        return gshape, [(rng.random(shape), W.shell_mask_slab(gshape, lo, hi))], (0.1,)
+        return gshape, [(_fill_random(rank), _fill_shell(gshape, lo, hi))], (0.1,)
     if name in ("conv1d", "conv1d_nl", "diff1d"):
         n = gshape[0]
         dx = 2.0 / (n - 1)
@@ -257,8 +281,8 @@ def cpu_arm(name: str, shape, budget_s: float, max_steps: int, sample_shape=None
     grids = []
     for ic, mask in inputs:
         g = oracle.HostGrid(shape)
-        g.now[...] = ic
-        g.boundary[...] = mask
+        _put(g.now, ic)
+        _put(g.boundary, mask)
         grids.append(g)
     rk = ref.KERNEL_OF.get(name)
     use_ref = (rk is not None and ref.available(rk) and os.environ.get("XGB_CPU_ARM", "reference") != "port"
@@ -331,8 +355,8 @@ class Arm:
         for ic, mask in inputs:
             g = self.xgrid.Grid(gshape, float)
             assert g.shape == tuple(shape), (g.shape, shape)
-            g.now[...] = ic
-            g.boundary[...] = mask
+            _put(g.now, ic)
+            _put(g.boundary, mask)
             out.append(g)
         return out
 
@@ -438,7 +462,7 @@ def e2e_legs(arm: Arm, name: str, kern, gshape, shape, inputs, scalars, K: int) 
         kern(*g2, *scalars)                        # first call uploads IC + mask (H2D)
     outs = [g.now for g in g2]                     # D2H of every grid's newest level (the rank's slab)
     dt = arm.max_over_ranks(time.perf_counter() - t0)
-    h2d = sum(ic.nbytes + mask.size * 4 for ic, mask in inputs)
+    h2d = sum(g.size * g.itemsize + g.size * 4 for g in g2)         # every grid's level + its int32 mask
     d2h = sum(o.nbytes for o in outs)
     out["e2e"] = {"value": points * world * spec["stmts"] * K / dt / 1e9, "unit": "Gpoint-updates/s",
                   "h2d_bytes_per_step": h2d * world / K, "d2h_bytes_per_step": d2h * world / K,
@@ -453,10 +477,8 @@ def e2e_legs(arm: Arm, name: str, kern, gshape, shape, inputs, scalars, K: int) 
         Ko = 3 if big else max(3, min(20, K))
         t0 = time.perf_counter()
         for _ in range(Ko):
-            for g, o in zip(g2, outs):
-                g.now[...] = o                     # host owns the level -> next call uploads it
-            kern(*g2, *scalars)
-            outs = [g.now for g in g2]
+            kern(*g2, *scalars)                    # the host owns every newest level (read below): uploads them
+            outs = [g.now for g in g2]             # D2H; hands the levels back to the host
         dt = time.perf_counter() - t0
         out["e2e_offload"] = {"value": points * spec["stmts"] * Ko / dt / 1e9, "unit": "Gpoint-updates/s",
                               "h2d_bytes_per_step": float(sum(o.nbytes for o in outs)),
@@ -652,7 +674,8 @@ def run_ours(args, rank: int, world: int):
     K = args.steps if args.steps is not None else spec["steps"]
     Wm = max(3, args.warmup if args.warmup is not None else spec["warmup"])
     arm = Arm(rank, world)
-    kern = arm.configure()[spec["kernel"]]
+    temporal, validate = not getattr(args, "no_temporal", False), not getattr(args, "fma", False)
+    kern = arm.configure(validate=validate, temporal=temporal)[spec["kernel"]]
     if world > 1:
         gshape, inputs, scalars = build_slab_inputs(name, shape, rank, world)
     else:
@@ -662,7 +685,10 @@ def run_ours(args, rank: int, world: int):
     # ---- device-resident throughput (`value`) ---------------------------------
     grids = arm.grids_for(gshape, shape, inputs)
     ms, launches, clocks, warm = device_leg(arm, kern, grids, scalars, K, Wm)
-    rec = record_of(arm, name, shape, K, ms, launches, clocks, warm)
+    rec = record_of(arm, name, shape, K, ms, launches, clocks, warm, temporal)
+    rec["config"]["validate_build"] = validate
+    if not temporal:
+        rec["config"]["temporal"] = False
     del grids
 
     # ---- end to end through the public API (`e2e`): host buffers -> K steps -> host result ----
@@ -701,6 +727,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-temporal", action="store_true", help="one launch per step (init(temporal=False))")
+    ap.add_argument("--fma", action="store_true", help="performance build (init(validate=False): FMA contraction)")
     ap.add_argument("--extra", default=None, help='sub-records at N=1: "all", "none" or a comma-separated list of keys '
                                                   '(default: all for --workload auto, none for a named workload)')
     args = ap.parse_args()

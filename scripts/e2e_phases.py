@@ -31,10 +31,10 @@ def job(tag):
     gs = [xgrid.Grid(shape, float) for _ in inputs]
     t.append(time.perf_counter())
     for g, (ic, mask) in zip(gs, inputs):
-        g.now[...] = ic
+        bench._put(g.now, ic)
     t.append(time.perf_counter())
     for g, (ic, mask) in zip(gs, inputs):
-        g.boundary[...] = mask
+        bench._put(g.boundary, mask)
     t.append(time.perf_counter())
     kern(*gs, *scalars)
     xgrid.flush()

@@ -477,3 +477,20 @@ def test_callee_operators_with_grids_run_their_own_sweeps_in_program_order(rt, t
     for _ in range(30):                                         # (the 4 buffers of u permute with a long period)
         mod.outer(u, v, 0.4)
     assert rt.graphs                                            # calls with callees are recorded and replayed too
+
+
+def test_first_upload_of_a_big_grid_packs_the_mask_while_the_levels_upload(rt):
+    k = W.make_kernels()["diffusion_1d"]
+    n = 1 << 22
+    u = xgrid.Grid((n,), float)
+    u.now[...] = 1.0
+    u.boundary[0] = u.boundary[-1] = 1
+    u.boundary[12345] = 9
+    k(u, 0.01, 0.1, 1.0)
+    xgrid.flush()
+    assert u._mask_any and u._mask_snapshot.dtype == np.uint8 and u._mask_snapshot.shape == (n,)
+    assert np.array_equal(np.flatnonzero(u._mask_snapshot), [0, 12345, n - 1]) and u._mask_snapshot[12345] == 9
+    assert u._mask_count(1) == 2 and u._mask_count(9) == 1 and u._mask_count(0) == n - 3
+    kinds = [c[0] for c in rt.copies]
+    assert kinds == ["h2d"] * 3                               # level 0, packed mask (n bytes), chunk flags
+    assert sorted(c[2] for c in rt.copies) == [n // 128, n, n * 8]

@@ -53,6 +53,34 @@ def parse_numpy_dtype(t: Value):
     return np.dtype(t.np_dtype)
 
 
+PACK_OVERLAP_MIN = 1 << 22   # points; below this the mask is packed in line
+
+
+class _PackJob:
+    """maskpack.pack on a helper thread (the C routine releases the GIL and runs its own worker threads)."""
+
+    def __init__(self, boundary: np.ndarray, n_padded: int) -> None:
+        import threading
+        from .runtime import maskpack
+        self._out, self._err = None, None
+        src = np.ascontiguousarray(boundary, np.int32)
+
+        def run() -> None:
+            try:
+                self._out = maskpack.pack(src, n_padded)
+            except BaseException as e:      # noqa: BLE001 -- re-raised on the calling thread
+                self._err = e
+
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def result(self):
+        self._thread.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
+
+
 class _Level:
     """One time level: device allocation + optional host mirror."""
     __slots__ = ("dev", "host", "where", "raw", "halo_rows", "halo_event", "pinned", "xfers", "view")
@@ -406,11 +434,16 @@ class Grid:
         """Make every level and the mask resident before launches."""
         if ghost_rows > self._ghost:
             self._ensure_ghost(ghost_rows)
+        job = None
+        if (self._mask_touched and self._mask_snapshot is None and self.size >= PACK_OVERLAP_MIN
+                and any(lv.where == "host" for lv in self._ring)):
+            # first upload of a big grid: pack the mask on host threads WHILE the levels cross PCIe
+            job = _PackJob(self._boundary, -(-self.size // CHUNK) * CHUNK)
         for lv in self._ring:
             if lv.where != "device":
                 self._to_device(lv)
         if self._mask_touched:
-            self._upload_mask()
+            self._upload_mask(job.result() if job is not None else None)
 
     def _scratch_level(self) -> _Level:
         if self._scratch is None or self._scratch.dev == 0:
@@ -449,7 +482,7 @@ class Grid:
             lv.where = "device"
 
     # ------------------------------------------------------------------ mask compilation
-    def _upload_mask(self) -> None:
+    def _upload_mask(self, prepacked=None) -> None:
         self._mask_touched = False
         b = self._boundary
         if self._mask_snapshot is not None and np.array_equal(b, self._mask_snapshot):
@@ -465,7 +498,7 @@ class Grid:
         nchunk = (self.size + CHUNK - 1) // CHUNK
         # pack on the host (several threads): one byte per point, chunk flags, histogram
         from .runtime import maskpack
-        packed, flags, hist, bad = maskpack.pack(np.ascontiguousarray(b, np.int32), nchunk * CHUNK)
+        packed, flags, hist, bad = prepacked or maskpack.pack(np.ascontiguousarray(b, np.int32), nchunk * CHUNK)
         if bad:
             self.logger.dead("boundary mask values must lie in [0, 254] on the B200 backend")
         # host copy for change detection / index lists / the fused-pair check: the packed bytes
