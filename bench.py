@@ -570,6 +570,27 @@ def parity_cases(arm: Arm) -> dict:
         oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
     check(f"cavity {nc}x{nc} x2 (622 sweeps)",
           [(gg.now, hh.now[s]) for gg, hh in zip(gs, hs)] + [(gg._data[1], hh._data[1][s]) for gg, hh in zip(gs, hs)])
+    # overstep modes on slabs: "wrap" turns the ranks into a ring, "limit" clamps at the global ends only;
+    # goldens produced by the unmodified reference (tests/golden/make_golden.py; square 32x32)
+    from examples import workloads as W2
+    for omode in ("wrap", "limit"):
+        path = os.path.join(ROOT, "tests", "golden", f"diff2d_{omode}_f64.npz")
+        if not os.path.exists(path):
+            continue
+        gd = np.load(path)
+        xgrid.init(precision="double", cacheroot=os.path.join(ROOT, ".xgrid"), device=arm.local_rank,
+                   distributed=world > 1, overstep=omode)
+        arm.mode = None                            # the next configure() re-initialises
+        ko = W2.make_kernels()["diffusion_2d_open"]
+        uo = xgrid.Grid(gd["u_in"].shape, float)
+        s = slab(uo)
+        uo.now[...] = gd["u_in"][s]
+        for _ in range(int(gd["steps"])):
+            ko(uo, float(gd["params"][0]))
+        check(f"diff2d overstep={omode} {'x'.join(map(str, gd['u_in'].shape))} x{int(gd['steps'])} (reference golden)",
+              [(uo.now, gd["u.L0"][s]), (uo._data[1], gd["u.L1"][s])])
+        del uo
+    arm.configure()
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -578,8 +599,8 @@ def parity_cases(arm: Arm) -> dict:
         for c, v in zip(cases, t.tolist()):
             c["ok"] = bool(v)
     return {"ok": all(c["ok"] for c in cases), "ranks": world, "bit_exact": True, "cases": cases,
-            "checker": "oracle/ (C restatement of the reference's generated loop nests, whole domain on every rank) vs "
-                       "each rank's slab, all ring levels"}
+            "checker": "oracle/ (C restatement of the reference's generated loop nests, whole domain on every rank) and "
+                       "reference-made goldens vs each rank's slab, all ring levels"}
 
 
 # --------------------------------------------------------------------------- sub-records (N = 1)

@@ -122,10 +122,6 @@ int xgb_occupancy(xgb_handle function, int block_threads, int dynamic_smem, int 
  * kernel takes ONE by-value parameter struct; `params` points at its bytes. */
 int xgb_launch(xgb_handle function, const uint32_t grid[3], const uint32_t block[3],
                uint32_t dynamic_smem, xgb_handle stream, const void *params, size_t param_bytes);
-/* same, with a thread-block cluster shape */
-int xgb_launch_cluster(xgb_handle function, const uint32_t grid[3], const uint32_t block[3],
-                       const uint32_t cluster[3], uint32_t dynamic_smem, xgb_handle stream,
-                       const void *params, size_t param_bytes);
 /* kernels launched through this ABI since xgb_init (graph replays count their
  * kernel nodes) */
 int xgb_launch_count(uint64_t *count);
@@ -135,12 +131,6 @@ int xgb_graph_begin(xgb_handle stream);
 int xgb_graph_end(xgb_handle stream, xgb_handle *graph_exec, int *kernel_nodes);
 int xgb_graph_launch(xgb_handle graph_exec, xgb_handle stream);
 int xgb_graph_destroy(xgb_handle graph_exec);
-
-/* ---- TMA descriptors ------------------------------------------------------ */
-/* 128-byte CUtensorMap for a dense row-major tensor of `rank` dims
- * (dims[0] = contiguous axis), box[] in elements, zero fill out of bounds. */
-int xgb_tensor_map_tiled(void *out_map_128B, int elem_bytes, int rank, void *base,
-                         const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);
 
 /* ---- multi-GPU: slab halo exchange (one process per GPU) ------------------ */
 /* new work, no reference counterpart. */

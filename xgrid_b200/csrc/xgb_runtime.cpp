@@ -2,9 +2,9 @@
 //
 // Host-side runtime of the B200 backend: device memory, streams/events, NVRTC
 // JIT (CUDA C -> sm_100a cubin), module/function handles, launches, CUDA graph
-// capture/replay, TMA descriptors and NCCL halo exchange.  Links the static CUDA
-// runtime only; the driver API (cuModule*, cuLaunchKernelEx,
-// cuTensorMapEncodeTiled), NVRTC and NCCL are resolved at run time so that the
+// capture/replay and NCCL halo exchange.  Links the static CUDA
+// runtime only; the driver API (cuModule*, cuLaunchKernelEx),
+// NVRTC and NCCL are resolved at run time so that the
 // library loads on a machine without a GPU (symbol / ABI checks) and fails
 // loudly -- never silently -- when a GPU call is made there.
 #include "../../include/xgrid_b200.h"
@@ -55,10 +55,6 @@ struct Driver {
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*LaunchKernelEx)(const CUlaunchConfig *, CUfunction, void **, void **) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
-    CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
 } drv;
 
 template <class F>
@@ -84,7 +80,6 @@ int load_driver() {
     if (load_entry("cuLaunchKernelEx", drv.LaunchKernelEx)) return 1;
     if (load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                    drv.OccupancyMaxActiveBlocksPerMultiprocessor)) return 1;
-    if (load_entry("cuTensorMapEncodeTiled", drv.TensorMapEncodeTiled)) return 1;
     drv.ready = true;
     return 0;
 }
@@ -697,8 +692,7 @@ int xgb_occupancy(xgb_handle function, int block_threads, int dynamic_smem, int 
 
 // ---- launch ---------------------------------------------------------------------
 static int launch_impl(xgb_handle function, const uint32_t grid[3], const uint32_t block[3],
-                       const uint32_t *cluster, uint32_t dynamic_smem, xgb_handle stream,
-                       const void *params) {
+                       uint32_t dynamic_smem, xgb_handle stream, const void *params) {
     if (require_init()) return 1;
     CUlaunchConfig cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -710,15 +704,6 @@ static int launch_impl(xgb_handle function, const uint32_t grid[3], const uint32
     cfg.blockDimZ = block[2];
     cfg.sharedMemBytes = dynamic_smem;
     cfg.hStream = reinterpret_cast<CUstream>(as_stream(stream));
-    CUlaunchAttribute attr[1];
-    if (cluster) {
-        attr[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
-        attr[0].value.clusterDim.x = cluster[0];
-        attr[0].value.clusterDim.y = cluster[1];
-        attr[0].value.clusterDim.z = cluster[2];
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-    }
     void *args[1] = {const_cast<void *>(params)};
     XGB_CU(drv.LaunchKernelEx(&cfg, reinterpret_cast<CUfunction>(function), args, nullptr));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -728,14 +713,7 @@ static int launch_impl(xgb_handle function, const uint32_t grid[3], const uint32
 int xgb_launch(xgb_handle function, const uint32_t grid[3], const uint32_t block[3],
                uint32_t dynamic_smem, xgb_handle stream, const void *params, size_t param_bytes) {
     (void)param_bytes;
-    return launch_impl(function, grid, block, nullptr, dynamic_smem, stream, params);
-}
-
-int xgb_launch_cluster(xgb_handle function, const uint32_t grid[3], const uint32_t block[3],
-                       const uint32_t cluster[3], uint32_t dynamic_smem, xgb_handle stream,
-                       const void *params, size_t param_bytes) {
-    (void)param_bytes;
-    return launch_impl(function, grid, block, cluster, dynamic_smem, stream, params);
+    return launch_impl(function, grid, block, dynamic_smem, stream, params);
 }
 
 int xgb_launch_count(uint64_t *count) {
@@ -797,34 +775,6 @@ int xgb_graph_destroy(xgb_handle graph_exec) {
     if (!g) return 0;
     if (g_device >= 0) cudaGraphExecDestroy(g->exec);
     delete g;
-    return 0;
-}
-
-// ---- TMA ------------------------------------------------------------------------
-int xgb_tensor_map_tiled(void *out_map_128B, int elem_bytes, int rank, void *base,
-                         const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
-    if (require_init()) return 1;
-    CUtensorMapDataType dt;
-    switch (elem_bytes) {
-        case 1: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
-        case 2: dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; break;
-        case 4: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
-        case 8: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT64; break;
-        default: return fail("xgb_tensor_map_tiled: unsupported element size");
-    }
-    if (rank < 1 || rank > 5) return fail("xgb_tensor_map_tiled: rank must be 1..5");
-    cuuint64_t gdim[5], gstr[5];
-    cuuint32_t bx[5], es[5];
-    for (int i = 0; i < rank; ++i) {
-        gdim[i] = dims[i];
-        bx[i] = box[i];
-        es[i] = 1;
-        if (i > 0) gstr[i - 1] = strides_bytes[i];  // stride of dim i (dim 0 is implicit)
-    }
-    XGB_CU(drv.TensorMapEncodeTiled(reinterpret_cast<CUtensorMap *>(out_map_128B), dt, (cuuint32_t)rank,
-                                    base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     return 0;
 }
 

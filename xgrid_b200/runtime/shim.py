@@ -77,15 +77,11 @@ SIGNATURES = {
     "xgb_function_set_dynamic_smem": [Handle, c_int],
     "xgb_occupancy": [Handle, c_int, c_int, POINTER(c_int)],
     "xgb_launch": [Handle, POINTER(c_uint32), POINTER(c_uint32), c_uint32, Handle, c_void_p, c_size_t],
-    "xgb_launch_cluster": [Handle, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32), c_uint32,
-                           Handle, c_void_p, c_size_t],
     "xgb_launch_count": [POINTER(c_uint64)],
     "xgb_graph_begin": [Handle],
     "xgb_graph_end": [Handle, POINTER(Handle), POINTER(c_int)],
     "xgb_graph_launch": [Handle, Handle],
     "xgb_graph_destroy": [Handle],
-    "xgb_tensor_map_tiled": [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint64), POINTER(c_uint64),
-                             POINTER(c_uint32)],
     "xgb_nccl_load": [c_char_p],
     "xgb_nccl_unique_id": [c_void_p],
     "xgb_nccl_init": [c_void_p, c_int, c_int],
