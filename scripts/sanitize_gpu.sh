@@ -22,4 +22,17 @@ pass synccheck smoke 400 python -c "$SMOKE"
 # tiled2 (two steps per pass), jacobi2 (fused solver pairs), 3-D tiled, short / tail multistep: small parity cases
 pass racecheck pipelines 900 python -m pytest tests/test_sanitize_cases_gpu.py -q -x -m gpu
 pass memcheck pipelines 600 python -m pytest tests/test_sanitize_cases_gpu.py -q -x -m gpu
+# control: the textbook single-stage bulk-copy + mbarrier pattern (correct by construction).  A report here means
+# racecheck does not model completion through mbarrier::complete_tx
+pass racecheck control 300 python -m pytest tests/test_racecheck_control_gpu.py -q -x -m gpu -k single_stage
+# control 2: a two-stage ring released through an "empty" mbarrier -- by ONE elected lane per warp after __syncwarp()
+# (the pipeline kernels' pattern, cumulative release) vs by EVERY consumer thread
+pass racecheck control_ring_elected_lane 300 python -m pytest tests/test_racecheck_control_gpu.py -q -x -m gpu -k ring_elected_lane
+pass racecheck control_ring_every_thread 300 python -m pytest tests/test_racecheck_control_gpu.py -q -x -m gpu -k ring_every_thread
+# individual hazards (type, thread, address): two steps per pass, fused pairs
+for case in two_steps fused_jacobi; do
+  NV_COMPUTE_SANITIZER_MAX_RACECHECK_HAZARDS=400000 timeout 900 compute-sanitizer --tool racecheck --racecheck-report hazard --print-limit 8000 \
+      --log-file $O/sanitize_racecheck_hazards_$case.log python -m pytest tests/test_sanitize_cases_gpu.py -q -x -m gpu -k "$case" > $O/sanitize_racecheck_hazards_$case.out 2>&1
+done
+python scripts/racecheck_classify.py $O/sanitize_racecheck_hazards_*.log $O/sanitize_racecheck_control*.log | tee $O/sanitize_racecheck_classes.txt
 cat $O/sanitize_summary.txt

@@ -28,7 +28,8 @@ def main() -> None:
     mask = np.zeros((n, n), np.int32)
     mask[0, :] = mask[-1, :] = mask[:, 0] = 1
     mask[:, -1] = 1
-    mask[7, 9] = 1
+    mask[1:-1, 0] = 2                           # Neumann column of `smooth` (reads its right neighbour at level 0)
+    mask[7, 9] = 1                              # value 2 has no statement in `relax` / `outer`: stale cells (F5)
     u, v = xgrid.Grid((n, n), float), xgrid.Grid((n, n), float)
     u.now[...] = u_in
     v.now[...] = v_in

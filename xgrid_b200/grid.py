@@ -471,6 +471,17 @@ class Grid:
         recorded CUDA graph was captured against / leaves behind."""
         return (tuple(lv.dev for lv in self._ring), self._scratch.dev if self._scratch is not None else 0)
 
+    def _halo_state(self) -> tuple:
+        """((device pointer, fresh ghost rows) of every ring level and the scratch level): slab grids only."""
+        levels = [*self._ring, *([self._scratch] if self._scratch is not None else [])]
+        return tuple((lv.dev, lv.halo_rows) for lv in levels)
+
+    def _restore_halo_state(self, state: tuple) -> None:
+        rows = dict(state)
+        for lv in [*self._ring, *([self._scratch] if self._scratch is not None else [])]:
+            lv.halo_rows = rows.get(lv.dev, 0)
+            lv.halo_event = 0
+
     def _restore_arrangement(self, arrangement: tuple) -> None:
         ring, scratch = arrangement
         pool = {lv.dev: lv for lv in self._ring}

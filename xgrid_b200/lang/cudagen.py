@@ -1233,8 +1233,13 @@ def tiled2_config(g: Group):
     if dmax - dmin > 4 or hk > 4:
         return None
     W = NCW * 32 * V * NSV
-    hkm = -(-hk // V) * V                 # halo of the middle rows
-    hk0 = -(-2 * hk // V) * V             # halo of the input rows
+    hkm = -(-hk // V) * V                 # halo of the middle rows (rounded up to whole vectors)
+    # halo of the input rows: EVERY middle element that is computed -- the rounded-up ones included -- must find
+    # its taps inside the loaded row.  (Round 1 used ceil(2*hk / V) * V, which equals hkm for hk = 1: the outermost
+    # middle vector then read one element past its input row -- into the next ring slot, or for the last slot into
+    # the first element of the middle ring.  The value was never used, but compute-sanitizer racecheck rightly
+    # reported the stray read against the write of that element, profiles/r2_sanitize.md.)
+    hk0 = -(-(hkm + hk) // V) * V
     wp0, wpm = W + 2 * hk0, W + 2 * hkm
     dspan = dmax - dmin
     mr = dspan + 2                        # middle-row ring

@@ -852,14 +852,22 @@ class Program:
 
         Launcher = _Launcher
         sharded = any(g.sharded for g in grids.values())
+        if sharded and self.config.graphs:
+            # a recorded call must be self-contained: no dependency may cross the capture boundary, so halo
+            # exchanges still in flight from the previous call are joined into the compute stream first (the
+            # next reader would wait for them anyway); the halo freshness of every level is part of the key
+            self._join_halo_events(grids)
         key = self._graph_key(env, grids) if (self.config.graphs and self.replayable()
-                                              and (self.groups or self.callees) and not sharded) else None
+                                              and (self.groups or self.callees)) else None
         hit = self._graphs.get(key) if key is not None else None
         if hit is not None:
-            # steady state: replay the recorded launches, then apply the recorded buffer permutation
+            # steady state: replay the recorded launches (on slabs: halo exchanges included), then apply the
+            # recorded buffer permutation and halo state
             self._runtime().graph_launch(hit["exec"])
             for name, g in grids.items():
                 g._restore_arrangement(hit["final"][name])
+                if g.sharded:
+                    g._restore_halo_state(hit["halo"][name])
             return hit["result"]
 
         launcher = Launcher(self, grids)
@@ -869,6 +877,8 @@ class Program:
             rt.graph_begin()
         try:
             result = _Interpreter(self.ir, env, grids, launcher, self.pairs).run(self.plan)
+            if record and sharded:
+                self._join_halo_events(grids)          # the communication stream re-joins the captured stream
         finally:
             if record:
                 graph, nodes = rt.graph_end()
@@ -883,7 +893,8 @@ class Program:
                 rt.graph_destroy(old["exec"])
                 del self._graphs[old_key]
             self._graphs[key] = {"exec": graph, "nodes": nodes, "result": result,
-                                 "final": {n: g._arrangement() for n, g in grids.items()}}
+                                 "final": {n: g._arrangement() for n, g in grids.items()},
+                                 "halo": {n: g._halo_state() for n, g in grids.items() if g.sharded}}
             rt.graph_launch(graph)          # the capture only recorded the work
         elif key is not None:
             self._seen.add(key)
@@ -895,6 +906,18 @@ class Program:
         if _Runtime is None:
             _late_imports()
         return _Runtime.get()
+
+    def _join_halo_events(self, grids: dict) -> None:
+        """Order the compute stream behind every halo exchange still in flight on the communication stream."""
+        rt = None
+        for g in grids.values():
+            if not g.sharded:
+                continue
+            for lv in [*g._ring, *([g._scratch] if g._scratch is not None else [])]:
+                if lv.halo_event:
+                    rt = rt or self._runtime()
+                    rt.stream_wait_event(0, lv.halo_event)
+                    lv.halo_event = 0
 
     def _run_batch2(self, args, grid, count: int) -> None:
         """2-D: `count` deferred identical calls, two time steps per pass (cudagen._emit_tiled2).
@@ -1040,6 +1063,8 @@ class Program:
                 # grid can get the very addresses a dead one had (caching pool, or cudaMalloc itself)
                 parts.append(grids[name]._arrangement() + (grids[name]._mask_version, grids[name].shape,
                                                            grids[name]._serial))
+                if grids[name].sharded:             # which exchanges a call issues depends on what is stale
+                    parts.append(grids[name]._halo_state())
             elif isinstance(t, Pointer):
                 parts.append(_deref(env[name]))
             elif isinstance(t, Structure):
