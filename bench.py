@@ -50,7 +50,7 @@ WORKLOADS = {
     "ewmul":     dict(kernel="elementwise_mul", ndim=1, shape=(10000,), stmts=1, bytes_pt=24, steps=2000, warmup=50),
 }
 MAIN = "heat3d"
-SHARDABLE = ("heat3d", "conv1d", "conv1d_nl", "diff1d")
+SHARDABLE = ("heat3d", "conv1d", "conv1d_nl", "diff1d", "cavity")
 
 
 def measured_peaks():
@@ -233,6 +233,12 @@ def build_slab_inputs(name: str, shape, rank: int, world: int):
                 mask[-1] = 1
             scalars = (0.01, 0.2 * dx * dx / 0.01, dx)
         return gshape, [(ic, mask)], scalars
+    if name == "cavity":
+        n0, n1 = gshape
+        dx, dy = 2.0 / (n1 - 1), 2.0 / (n0 - 1)
+        dt = 1e-4 * (100.0 / (n1 - 1)) ** 2
+        z = np.zeros(shape)
+        return gshape, [(z, m) for m in W.cavity_masks_slab(n0, n1, lo, hi)], (W.Config(1.0, 0.1, dt, dx, dy),)
     raise SystemExit("multi-GPU bench is defined for the slab-sharded workloads: " + ", ".join(SHARDABLE))
 
 
@@ -328,7 +334,8 @@ class Arm:
         from examples import workloads as W
         if self.mode != (validate, temporal):
             self.xgrid.init(precision="double", cacheroot=os.path.join(ROOT, ".xgrid"), device=self.local_rank,
-                            distributed=self.world > 1, validate=validate, temporal=temporal)
+                            distributed=self.world > 1, validate=validate, temporal=temporal,
+                            graphs=os.environ.get("XGB_BENCH_GRAPHS", "1") != "0")
             self.kernels = W.make_kernels()
             self.mode = (validate, temporal)
         return self.kernels

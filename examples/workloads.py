@@ -195,6 +195,28 @@ def shell_mask_slab(global_shape, lo: int, hi: int, value: int = 1) -> np.ndarra
     return m
 
 
+def cavity_masks_slab(n0: int, n1: int, lo: int, hi: int):
+    """Rows [lo, hi) of cavity_masks(n0, n1) without materialising the global masks."""
+    rows = hi - lo
+    first, last = (lo == 0), (hi == n0)
+    mu = np.zeros((rows, n1), np.int32)
+    mu[:, 0] = 1
+    mu[:, -1] = 1
+    if first:
+        mu[0, :] = 1
+    if last:
+        mu[-1, :] = 2
+    mv = shell_mask_slab((n0, n1), lo, hi)
+    mp = np.zeros((rows, n1), np.int32)
+    mp[:, -1] = 1
+    if first:
+        mp[0, :] = 2
+    mp[:, 0] = 3
+    if last:
+        mp[-1, :] = 4
+    return mv.copy(), mp, mu, mv
+
+
 def cavity_masks(n0: int, n1: int):
     """examples/cavity.py:56-68 -> (mb, mp, mu, mv)"""
     mu = np.zeros((n0, n1), np.int32)

@@ -199,7 +199,7 @@ def main():
         for gg, hh, m in zip(gs, hs, (mb, mp, mu, mv)):
             gg.boundary[...] = m[loc:hic]
             hh.boundary[...] = m
-        for _ in range(2):
+        for _ in range(7):
             k["cavity_kernel"](*gs, cfg)
             oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
         for gg, hh in zip(gs, hs):
