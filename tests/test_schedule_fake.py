@@ -462,6 +462,7 @@ def test_callee_operators_with_grids_run_their_own_sweeps_in_program_order(rt, t
     u, v = xgrid.Grid((24, 24), float), xgrid.Grid((24, 24), float)
     u.boundary[0, :] = 1
     v.boundary[0, :] = 1
+    u.boundary[1:-1, 0] = 2                                   # `smooth`'s Neumann column
     mod.outer(u, v, 0.4)
     assert mod.outer.depth == 3 and len(u._ring) == len(v._ring) == 3
     names = [n.split("_g")[0] for n in rt.names()]

@@ -772,6 +772,9 @@ TILED_SMEM_BUDGET = int(_os.environ.get("XGB_SMEM", "0"))      # 0 = per-dimensi
 TILED_TJ = int(_os.environ.get("XGB_TJ", "8"))
 TILED_WX3 = int(_os.environ.get("XGB_WX3", "1"))       # consumer warps side by side along k in 3-D
 TILED_NSV = int(_os.environ.get("XGB_NSV", "0"))         # 0 = per-dimension default below
+TILED_BATCH = _os.environ.get("XGB_TILED_BATCH", "1") != "0"   # all-interior iterations: loads of every vector first
+TILED_BATCH_MAX = int(_os.environ.get("XGB_TILED_BATCH_MAX", "56"))  # ... if the windows of all vectors fit this many fp64 registers
+TILED_MINB = int(_os.environ.get("XGB_TILED_MINB", "0"))       # __launch_bounds__ min CTAs per SM (0 = unset)
 TILED_WX2 = int(_os.environ.get("XGB_WX2", "0"))         # consumer warps per CTA in 2-D; 0 = by stream count
 # measured on B200 (profiles/r1_experiments.md): 2-D likes 2 vectors per thread and ~56 KB rings
 # (4 CTAs/SM); 3-D amortises the per-plane bookkeeping better with 4 vectors per thread (256-column
@@ -852,7 +855,8 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
         return f"{wnames[key]}[v + {e.space_offset[-1] - lo}]"
 
     name = kernel_name(g, VARIANT_TILED, V)
-    L = [f'extern "C" __global__ void __launch_bounds__({c["threads"]}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
+    bounds = f'{c["threads"]}, {TILED_MINB}' if TILED_MINB else f'{c["threads"]}'
+    L = [f'extern "C" __global__ void __launch_bounds__({bounds}) {name}(const __grid_constant__ {g.name}_P p)', "{"]
     L.append(f"    constexpr int V = {V}, NSV = {NSV}, NCW = {c['NCW']}, TJ = {c['TJ']}, WX = {c['WX']}, W = {c['W']};")
     L.append(f"    constexpr int HJ = {c['HJ']}, HK = {c['HK']}, WP = {c['WP']}, RP = {c['RP']}, NS = {c['NS']};")
     L.append(f"    constexpr int DMIN = {c['DMIN']}, DMAX = {c['DMAX']}, DSPAN = DMAX - DMIN, NREAD = {c['NREAD']};")
@@ -970,10 +974,57 @@ def _emit_tiled(g: Group, module: ModuleBuilder, c: dict) -> str:
             if sl not in fast_written:
                 fast_written.append(sl)
     _emit_statements(g, module, tap, slow_body, "v", hoist)
+    flags_zero = " && ".join(f"fc_{m}[sv] == 0" for m in g.masks) or "true"
+    batch_doubles = NSV * sum(V + hi - lo for lo, hi in windows.values()) * (read_slots[0].elem.width_bytes / 8.0)
+    # (3-D only: the 2-D one-pass kernels run at 0.96-0.97 of the copy peak as they are, and the multi-statement
+    # cavity groups would go from 128 to 194 registers)
+    if TILED_BATCH and nd == 3 and NSV > 1 and fast_body and batch_doubles <= TILED_BATCH_MAX:
+        # The common iteration -- every vector of this thread active and no boundary point near the warp's spans --
+        # runs WITHOUT a branch per vector: all shared-memory windows are requested first, then all vectors are
+        # computed, then all are stored, so the loads of NSV vectors overlap instead of each vector paying its own
+        # load -> fp64 chain -> store latency in turn (ncu, round 2: consumers were never starved for data -- 1.5 % of
+        # stall samples on the "full" barrier -- but only 38 % of issue slots were used at 16 consumer warps per SM).
+        def tapb(e: ir.Stencil) -> str:
+            slot = g.slot(e.variable.name, e.level)
+            key = (slot.index, e.space_offset[0], e.space_offset[1] if nd == 3 else 0)
+            lo, _ = windows[key]
+            return f"{wnames[key]}b[sv][v + {e.space_offset[-1] - lo}]"
+
+        emitb = ExprEmitter(module, _ident, tapb, hoist, VARIANT_TILED)
+        L.append("        bool allfast = true;")
+        L.append("#pragma unroll")
+        L.append(f"        for (int sv = 0; sv < NSV; ++sv) allfast = allfast && act[sv] && ({flags_zero});")
+        L.append("        if (allfast) {")
+        for key, (lo, hi) in windows.items():
+            L.append(f"            T {wnames[key]}b[NSV][V + {hi - lo}];")
+        L.append("#pragma unroll")
+        L.append("            for (int sv = 0; sv < NSV; ++sv) {")
+        for key, (lo, hi) in windows.items():
+            si, di, dj = key
+            L.append(f"                xgb::lds_window<T, V, {lo}, {hi}>(pl{di - c['DMIN']} + ({ridx[si]} * RP + ({dj})) * WP + kk[sv], {wnames[key]}b[sv]);")
+        L.append("            }")
+        for sl in fast_written:
+            L.append(f"            {module.ctype(sl.elem)} o_{sl.field}b[NSV][V];")
+        L.append("#pragma unroll")
+        L.append("            for (int sv = 0; sv < NSV; ++sv) {")
+        L.append("#pragma unroll")
+        L.append("                for (int v = 0; v < V; ++v) {")
+        for a in g.stmts:
+            if a.sweep.mask == 0:
+                sl = g.slot(a.sweep.grid.name, "scratch" if g.implicit else a.sweep.store.level)
+                L.append(f"                    o_{sl.field}b[sv][v] = {emitb(a.value)};")
+        L.append("                }")
+        L.append("            }")
+        L.append("#pragma unroll")
+        L.append("            for (int sv = 0; sv < NSV; ++sv) {")
+        for sl in fast_written:
+            L.append(f"                xgb::st_vec<{module.ctype(sl.elem)}, V>(p.{sl.field} + base[sv], o_{sl.field}b[sv]);")
+        L.append("                base[sv] += S0;")
+        L.append("            }")
+        L.append("        } else")
     L.append("#pragma unroll")
     L.append("        for (int sv = 0; sv < NSV; ++sv) {")
     L.append("            if (act[sv]) {")
-    flags_zero = " && ".join(f"fc_{m}[sv] == 0" for m in g.masks) or "true"
     L.append(f"                if ({flags_zero}) {{            // no boundary point in this 128-point chunk")
     L.extend(load_windows("                    "))
     for sl in fast_written:
