@@ -80,11 +80,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device: int) -> None:
+    def __init__(self, device: int, enabled: bool = True) -> None:
         self.device, self.rows, self.proc = device, [], None
         self.t0 = self.t1 = None
+        self.enabled = enabled          # rank 0 samples its GPU; eight pollers on one box only perturb it
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -357,6 +360,16 @@ class Arm:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(self, x: float) -> list:
+        if self.world == 1:
+            return [x]
+        import torch
+        import torch.distributed as dist
+        t = torch.zeros(self.world, dtype=torch.float64, device=f"cuda:{self.local_rank}")
+        t[self.rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def grids_for(self, gshape, shape, inputs):
         out = []
         for ic, mask in inputs:
@@ -376,7 +389,7 @@ def device_leg(arm: Arm, kern, grids, scalars, K: int, Wm: int):
     Returns (ms max over ranks, launches, clocks summary, warm-up steps)."""
     rt = arm.rt
     reps = max(1, -(-Wm // K))
-    with ClockSampler(arm.local_rank) as clocks:
+    with ClockSampler(arm.local_rank, enabled=arm.rank == 0) as clocks:
         for _ in range(reps):
             for _ in range(K):
                 kern(*grids, *scalars)
@@ -395,8 +408,11 @@ def device_leg(arm: Arm, kern, grids, scalars, K: int, Wm: int):
     rt.device_sync()
     arm.barrier()
     launches = rt.launch_count() - n0
-    ms = arm.max_over_ranks(rt.event_elapsed_ms(ev0, ev1))
-    return ms, int(launches), clocks.summary(), reps * K
+    per_rank = arm.all_ranks(rt.event_elapsed_ms(ev0, ev1))
+    summary = clocks.summary()
+    if arm.world > 1:
+        summary["ms_per_step_by_rank"] = [round(v / K, 4) for v in per_rank]     # `ms_per_step` is their maximum
+    return max(per_rank), int(launches), summary, reps * K
 
 
 def traffic_of(name: str, shape, launches: int, K: int, temporal: bool = True):
