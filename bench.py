@@ -593,6 +593,31 @@ def parity_cases(arm: Arm) -> dict:
         oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
     check(f"cavity {nc}x{nc} x2 (622 sweeps)",
           [(gg.now, hh.now[s]) for gg, hh in zip(gs, hs)] + [(gg._data[1], hh._data[1][s]) for gg, hh in zip(gs, hs)])
+    # cavity wide enough for the fused Jacobi pairs: on slabs the fused pass covers the interior rows, the three rows
+    # next to each cut run step-at-a-time on row bands (lang/launch.py::run_pair)
+    from xgrid_b200.lang.launch import STATS
+    n0c, n1c = 64 * max(world, 2), 640
+    mb, mp, mu, mv = W.cavity_masks(n0c, n1c)
+    cfg = W.Config(1.0, 0.1, 1e-4 * (100.0 / (n1c - 1)) ** 2, 2.0 / (n1c - 1), 2.0 / (n0c - 1))
+    gs = [xgrid.Grid((n0c, n1c), float) for _ in range(4)]
+    hs = [oracle.HostGrid((n0c, n1c)) for _ in range(4)]
+    s = slab(gs[0])
+    rngc = np.random.default_rng(5)
+    for gg, hh, m in zip(gs, hs, (mb, mp, mu, mv)):
+        icc = 1e-3 * rngc.random((n0c, n1c))
+        gg.now[...] = icc[s]
+        hh.now[...] = icc
+        gg.boundary[...] = m[s]
+        hh.boundary[...] = m
+    fused_before = STATS.get("jacobi2", 0)
+    for _ in range(3):
+        k["cavity_kernel"](*gs, cfg)
+        oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
+    fused = STATS.get("jacobi2", 0) - fused_before
+    check(f"cavity {n0c}x{n1c} x3 ({fused} fused Jacobi pairs)",
+          [(gg.now, hh.now[s]) for gg, hh in zip(gs, hs)] + [(gg._data[1], hh._data[1][s]) for gg, hh in zip(gs, hs)]
+          + [(fused, 72)])
+    del gs, hs
     # overstep modes on slabs: "wrap" turns the ranks into a ring, "limit" clamps at the global ends only;
     # goldens produced by the unmodified reference (tests/golden/make_golden.py; square 32x32)
     from examples import workloads as W2

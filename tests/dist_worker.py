@@ -204,6 +204,28 @@ def main():
             oracle.step_cavity(*hs, oracle.Config(cfg.rho, cfg.nu, cfg.dt, cfg.dx, cfg.dy))
         for gg, hh in zip(gs, hs):
             ok = ok and np.array_equal(gg.now, hh.now[loc:hic]) and np.array_equal(gg._data[1], hh._data[1][loc:hic])
+        # fused Jacobi pairs on slabs: grid wide enough for the fused pass (>= 512 columns); interior rows fused, the
+        # three rows next to the cut on row bands
+        n0c, n1c = 128, 640
+        mb, mp, mu, mv = W.cavity_masks(n0c, n1c)
+        cfgc = W.Config(1.0, 0.1, 1e-4 * (100.0 / (n1c - 1)) ** 2, 2.0 / (n1c - 1), 2.0 / (n0c - 1))
+        gs = [xgrid.Grid((n0c, n1c), float) for _ in range(4)]
+        hs = [HostGrid((n0c, n1c)) for _ in range(4)]
+        loc, hic = gs[0].row_range
+        rngc = np.random.default_rng(5)
+        for gg, hh, m in zip(gs, hs, (mb, mp, mu, mv)):
+            icc = 1e-3 * rngc.random((n0c, n1c))
+            gg.now[...] = icc[loc:hic]
+            hh.now[...] = icc
+            gg.boundary[...] = m[loc:hic]
+            hh.boundary[...] = m
+        fused0 = STATS.get("jacobi2", 0)
+        for _ in range(5):
+            k["cavity_kernel"](*gs, cfgc)
+            oracle.step_cavity(*hs, oracle.Config(cfgc.rho, cfgc.nu, cfgc.dt, cfgc.dx, cfgc.dy))
+        ok = ok and STATS.get("jacobi2", 0) - fused0 == 5 * 24
+        for gg, hh in zip(gs, hs):
+            ok = ok and np.array_equal(gg.now, hh.now[loc:hic]) and np.array_equal(gg._data[1], hh._data[1][loc:hic])
         # overstep modes on slabs: ring ("wrap") / chain with clamping at the global ends ("limit");
         # golden produced by the reference (square 32x32) and a non-square NumPy restatement
         gold_dir = os.path.join(ROOT, "tests", "golden")

@@ -45,7 +45,7 @@ def test_bench_line_has_the_contract_keys(monkeypatch, tmp_path, workload, shape
     assert line["warmup"] % steps == 0 and line["warmup"] >= 3
     if workload == "heat3d":
         # the parity field's code path runs (its verdict is meaningless on the fake runtime: nothing executes)
-        assert {"ok", "ranks", "cases", "checker"} <= set(line["parity"]) and len(line["parity"]["cases"]) >= 4
+        assert {"ok", "ranks", "cases", "checker"} <= set(line["parity"]) and len(line["parity"]["cases"]) >= 5
 
 
 def test_default_workload_is_the_3d_slab_at_every_n_and_both_arms_print_the_same_config():

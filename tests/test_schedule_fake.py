@@ -534,3 +534,49 @@ def test_sharded_calls_are_recorded_and_replayed_with_their_halo_state(monkeypat
         assert a == b, f"launch {i} differs:\n{a}\n{b}"
     assert st_g == st_d                                        # same freshness of every level after every call
     assert ex_g < ex_d                                         # replayed calls issue their exchanges from the graph
+
+
+def test_fused_jacobi_pairs_on_a_slab_cover_the_interior_and_leave_bands_to_single_sweeps(monkeypatch, tmp_path):
+    """Middle rank of 4: per fused pair the rows that need nothing from a neighbour run in the fused kernel; the 3 rows
+    next to each cut run sweep A (two rows deeper) into a third buffer, the boundary statements on it, and sweep B
+    into the output buffer, all with the ordinary kernels on row bands."""
+    from xgrid_b200.lang.launch import SLAB_BAND
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True, graphs=False)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    k = W.make_kernels()["cavity_kernel"]
+    n, cols = 4 * 256, 1024
+    masks = W.cavity_masks(n, cols)
+    gs = [xgrid.Grid((n, cols), float) for _ in range(4)]
+    for g, m in zip(gs, masks):
+        g.boundary[...] = m[g.row_range[0]:g.row_range[1]]
+    cfg = W.Config(1.0, 0.1, 1e-4, 2.0 / (cols - 1), 2.0 / (n - 1))
+    k(*gs, cfg)
+    n0 = gs[1].shape[0]
+    fused = [r for r in rt.launches if "jacobi2" in r[0]]
+    assert len(fused) == 24 and SLAB_BAND == 3
+    assert all((r[3]["r_lo"], r[3]["r_hi"]) == (3, n0 - 3) for r in fused)
+    p = gs[1]
+    first = rt.launches.index(fused[0])
+    # the launches right before the first fused pass: sweep A on [0,5) and [n0-5,n0), boundary statements (this rank
+    # owns boundary points of the two side columns only: masks 1 and 3), sweep B on [0,3) and [n0-3,n0)
+    before = rt.launches[:first]
+    bands = [(r[3]["r_lo"], r[3]["r_hi"]) for r in before if r[0].startswith("xg_cavity_kernel_g6_") and "sparse" not in r[0]]
+    assert bands[-4:] == [(0, 5), (n0 - 5, n0), (0, 3), (n0 - 3, n0)], bands
+    a_band, b_band = before[-6 - 0], before[-1]      # (sparse launches sit between the two pairs of band sweeps)
+    x, s = fused[0][3]["s1"], fused[0][3]["s0"]
+    ptrs = lambda r: {v for kk, v in r[3].items() if kk.startswith("s") and isinstance(v, int)}      # noqa: E731
+    assert x in ptrs(before[[i for i, r in enumerate(before) if (r[3].get("r_lo"), r[3].get("r_hi")) == (0, 5)][-1]])
+    assert s in ptrs(b_band) and x not in ptrs(b_band)          # sweep B reads the third buffer, writes the output buffer
+    third = (ptrs(b_band) - {s}) & {lv.dev for lv in p._spares}
+    assert len(third) == 1
+    # the ring is intact afterwards: the third buffer never enters it
+    assert third.isdisjoint({lv.dev for lv in p._ring}) and third.isdisjoint({p._scratch.dev})
+    # rank 0 of the chain has no lower neighbour: its fused pass starts at row 0
+    rt0, tr0 = fake_runtime.install_sharded(monkeypatch, rank=0, world=4)
+    k = W.make_kernels()["cavity_kernel"]                     # (function handles belong to a runtime)
+    gs0 = [xgrid.Grid((n, cols), float) for _ in range(4)]
+    for g, m in zip(gs0, masks):
+        g.boundary[...] = m[g.row_range[0]:g.row_range[1]]
+    k(*gs0, cfg)
+    f0 = [r for r in rt0.launches if "jacobi2" in r[0]]
+    assert len(f0) == 24 and all((r[3]["r_lo"], r[3]["r_hi"]) == (0, gs0[1].shape[0] - 3) for r in f0)

@@ -819,7 +819,7 @@ def tiled_config(g: Group):
         return None
     stage_bytes = nread * rp * wp * esize
     ns = min(8, max((dmax - dmin) + 3, (budget - 256) // stage_bytes))
-    if 256 + ns * stage_bytes > 200 * 1024:
+    if 256 + ns * stage_bytes > 224 * 1024:            # 227 KB per CTA on sm_100a, 1 KB of it static
         return None
     return {"V": V, "NSV": NSV, "NCW": ncw, "TJ": tj, "WX": wx, "W": W, "HJ": hj, "HK": hk, "WP": wp,
             "RP": rp, "NS": ns, "DMIN": dmin, "DMAX": dmax, "NREAD": nread, "ESIZE": esize,

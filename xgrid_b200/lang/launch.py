@@ -98,6 +98,7 @@ def tiled_geometry(shape, t: dict):
 
 
 STATS: dict = {}          # kernel variant -> launches (diagnostics / tests)
+SLAB_BAND = jacobi2.HA + jacobi2.DR + jacobi2.HA      # rows next to a slab cut whose fused-pair value needs the neighbour
 
 
 def full_grid_variant(g: cudagen.Group, shape) -> tuple:
@@ -148,11 +149,18 @@ class Launcher:
         g = pair.sweep
         lead = self.grids[g.lead]
         c = pair.config
-        if lead.sharded or lead.dimension != 2:
+        if lead.dimension != 2:
             return False
         n0, cols = lead.shape
         if cols % c["V"] or cols < jacobi2.MIN_COLS or n0 < jacobi2.MIN_ROWS:
             return False
+        if lead.sharded:
+            # a slab keeps SLAB_BAND rows per cut for the step-at-a-time path, run on row bands by a variant
+            # that honours them
+            if n0 < 2 * (SLAB_BAND + 2) + jacobi2.MIN_ROWS:
+                return False
+            if full_grid_variant(g, lead.shape)[0] not in (cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH):
+                return False
         if any(self.grids[s.grid].shape != lead.shape for s in g.slots):
             return False
         if not lead._mask_any:
@@ -166,15 +174,44 @@ class Launcher:
         return ok
 
     def run_pair(self, pair, env: dict) -> None:
+        """Sweep A, boundary statements, sweep B in one pass; then the boundary statements after B.
+        On a slab the fused pass covers the rows that need nothing from a neighbour: output rows
+        [SLAB_BAND, n0 - SLAB_BAND) read input rows of this slab only (sweep A reaches HA rows, a boundary
+        copy chain DR more, sweep B HA again).  The SLAB_BAND rows next to each cut run step-at-a-time on
+        row bands with the ordinary kernels -- sweep A into a third buffer T (two rows deeper than the band,
+        so that its boundary statements and sweep B find their taps), the boundary statements on T (halo
+        refreshed by the usual planner), sweep B from T into the output buffer -- with the buffers' roles
+        re-pointed, never copied.  Every value is produced by the same expression text either way."""
         g, c = pair.sweep, pair.config
         lead = self.grids[g.lead]
-        P = self._params(g, env)
         n0, cols = lead.shape
+        r_lo, r_hi = 0, n0
+        if lead.sharded:
+            from .. import dist
+            topo = dist.topology()
+            lo_band = SLAB_BAND if topo.lo_rank >= 0 else 0
+            hi_band = SLAB_BAND if topo.hi_rank >= 0 else 0
+            r_lo, r_hi = lo_band, n0 - hi_band
+            if lo_band or hi_band:
+                X, S = lead._ring[0], lead._scratch_level()
+                T = lead._spare_levels(1)[0]
+                deep = [(0, lo_band + 2)] * bool(lo_band) + [(n0 - hi_band - 2, n0)] * bool(hi_band)
+                edge = [(0, lo_band)] * bool(lo_band) + [(n0 - hi_band, n0)] * bool(hi_band)
+                try:
+                    lead._scratch = T
+                    self(g, env, bands=deep)                 # sweep A on the bands: X -> T
+                    lead._ring[0], lead._scratch = T, S
+                    for r in pair.rules:                     # boundary statements A, on T
+                        self(r.group, env)
+                    self(g, env, bands=edge)                 # sweep B on the bands: T -> S
+                finally:
+                    lead._ring[0], lead._scratch = X, S
+        P = self._params(g, env)
         gx = (cols + c["W"] - 1) // c["W"]
         want = max(1, -(-TUNE["min_ctas"] // gx))
-        chunk0 = jacobi2.CHUNK0 or max(32, -(-n0 // want))     # measured: 32 beats 64 / 128 (tail effect)
-        chunks = (n0 + chunk0 - 1) // chunk0
-        P.chunk0, P.r_lo, P.r_hi = chunk0, 0, n0
+        chunk0 = jacobi2.CHUNK0 or max(32, -(-(r_hi - r_lo) // want))     # measured: 32 beats 64 / 128 (tail effect)
+        chunks = (r_hi - r_lo + chunk0 - 1) // chunk0
+        P.chunk0, P.r_lo, P.r_hi = chunk0, r_lo, r_hi
         gy = min(chunks, 65535)
         fn = self.program.function(cudagen.kernel_name(g, jacobi2.VARIANT, c["V"]), c["smem"])
         self.rt.launch(fn, (gx, gy, (chunks + gy - 1) // gy), (c["threads"], 1, 1), P, smem=c["smem"])
@@ -247,7 +284,9 @@ class Launcher:
             setattr(P, f"u_{name}", self._scalar_value(t, env[name]))
         return P
 
-    def __call__(self, g: cudagen.Group, env: dict) -> None:
+    def __call__(self, g: cudagen.Group, env: dict, bands=None) -> None:
+        """One sweep group.  `bands`: only these axis-0 row ranges, no edge-first overlap and no scratch swap
+        (the slab path of the fused solver pairs drives the buffers itself)."""
         lead = self.grids[g.lead]
         P = self._params(g, env)
         shape = lead.shape
@@ -297,6 +336,11 @@ class Launcher:
                 self.rt.stream_wait_event(0, lv.halo_event)
                 lv.halo_event = 0
         edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)
+        if bands is not None:
+            for lo, hi in bands:
+                launch_rows(lo, hi)
+            self._mark_written(g)
+            return
         if (edge and TUNE["overlap"] and variant in (cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH)
                 and shape[0] >= 8 * edge):
             # slab edges first, then ship the fresh rows to the neighbours on the comm stream
