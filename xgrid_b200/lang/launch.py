@@ -127,6 +127,7 @@ class Launcher:
         self.grids = grids
         self._rt = None
         self.launches = 0
+        self.stream = 0             # where sweeps are enqueued (the slab path of the fused pairs uses a side stream)
 
     @property
     def rt(self):
@@ -197,7 +198,13 @@ class Launcher:
                 T = lead._spare_levels(1)[0]
                 deep = [(0, lo_band + 2)] * bool(lo_band) + [(n0 - hi_band - 2, n0)] * bool(hi_band)
                 edge = [(0, lo_band)] * bool(lo_band) + [(n0 - hi_band, n0)] * bool(hi_band)
+                # the band chain (a dozen small launches and two halo exchanges) runs on a high-priority side
+                # stream BESIDE the fused pass of the interior: it reads X like the fused pass and writes other rows
+                side, fork, join = self.rt.side_stream()
+                self.rt.event_record_raw(fork, 0)
+                self.rt.stream_wait_event(side, fork)
                 try:
+                    self.stream = side
                     lead._scratch = T
                     self(g, env, bands=deep)                 # sweep A on the bands: X -> T
                     lead._ring[0], lead._scratch = T, S
@@ -205,7 +212,9 @@ class Launcher:
                         self(r.group, env)
                     self(g, env, bands=edge)                 # sweep B on the bands: T -> S
                 finally:
+                    self.stream = 0
                     lead._ring[0], lead._scratch = X, S
+                self.rt.event_record_raw(join, side)
         P = self._params(g, env)
         gx = (cols + c["W"] - 1) // c["W"]
         want = max(1, -(-TUNE["min_ctas"] // gx))
@@ -217,6 +226,8 @@ class Launcher:
         self.rt.launch(fn, (gx, gy, (chunks + gy - 1) // gy), (c["threads"], 1, 1), P, smem=c["smem"])
         self.launches += 1
         STATS[jacobi2.VARIANT] = STATS.get(jacobi2.VARIANT, 0) + 1
+        if lead.sharded and r_lo + (n0 - r_hi):
+            self.rt.stream_wait_event(0, join)           # the bands of the output buffer are complete
         self._mark_written(g)
         lead._swap_scratch()
         for r in pair.rules:                 # boundary statements of the second iteration
@@ -323,7 +334,7 @@ class Launcher:
                 block_dim, grid_dim = (128, 1, 1), ((P.count + 127) // 128, 1, 1)
             else:
                 grid_dim, block_dim = dense_geometry(rows, cols, V)
-            self.rt.launch(fn, grid_dim, block_dim, P, smem=smem)
+            self.rt.launch(fn, grid_dim, block_dim, P, smem=smem, stream=self.stream)
             self.launches += 1
             STATS[variant] = STATS.get(variant, 0) + 1
 
@@ -333,7 +344,7 @@ class Launcher:
             # the comm stream (nothing read its ghost rows in between): order this sweep behind it
             lv = gr._scratch if s.level == "scratch" else gr._ring[s.level]
             if gr.sharded and lv is not None and lv.halo_event:
-                self.rt.stream_wait_event(0, lv.halo_event)
+                self.rt.stream_wait_event(self.stream, lv.halo_event)
                 lv.halo_event = 0
         edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)
         if bands is not None:
@@ -381,9 +392,9 @@ class Launcher:
                 grid = self.grids[s.grid]
                 lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
                 if grid.sharded and lv.halo_event:
-                    self.rt.stream_wait_event(0, lv.halo_event)
+                    self.rt.stream_wait_event(self.stream, lv.halo_event)
                     lv.halo_event = 0
                 reads.append((grid, lv, s.halo0))
         stale = dist.HaloPlan.stale(reads)
         if stale:
-            dist.transport().exchange(stale)
+            dist.transport().exchange(stale, self.stream)

@@ -255,6 +255,13 @@ class Runtime:
         check(self.l.xgb_stream_create_ex(C.byref(h), 1 if high_priority else 0))
         return h.value
 
+    def side_stream(self):
+        """(high-priority side stream, fork event, join event): work that may run beside the compute stream."""
+        side = getattr(self, "_side", None)
+        if side is None:
+            side = self._side = (self.stream_create(high_priority=True), self.event_create(), self.event_create())
+        return side
+
     def stream_raw(self, stream: int = 0) -> int:
         p = c_void_p()
         check(self.l.xgb_stream_raw(stream, C.byref(p)))
