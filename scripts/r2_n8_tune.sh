@@ -19,7 +19,8 @@ PY
 {
 run "default" A=1
 run "NCCL_MAX_NCHANNELS=4" NCCL_MAX_NCHANNELS=4
-run "NCCL_MAX_NCHANNELS=2" NCCL_MAX_NCHANNELS=2
 run "overlap off" XGB_OVERLAP=0
 run "default (repeat)" A=1
+echo "== cavity 8192^2 over 8 GPUs (fused pairs on slabs)"
+timeout 300 $TR bench.py --gpus 8 --workload cavity --shape 1024 8192 --steps 6 --warmup 4 --no-e2e > $O/r2h_n8_cavity.json 2>$O/r2h_n8_cavity.err; tail -c 900 $O/r2h_n8_cavity.json
 } 2>&1 | tee $O/r2h_n8_tune.txt
