@@ -528,12 +528,16 @@ def test_sharded_calls_are_recorded_and_replayed_with_their_halo_state(monkeypat
         traces.append((list(rt.launches), states, len(rt.graphs), len(tr.log)))
         del grids
     (with_graphs, st_g, n_graphs, ex_g), (direct, st_d, none, ex_d) = traces
-    assert none == 0 and n_graphs >= 1, "sharded calls were not recorded"
     assert len(with_graphs) == len(direct)
     for i, (a, b) in enumerate(zip(with_graphs, direct)):
         assert a == b, f"launch {i} differs:\n{a}\n{b}"
     assert st_g == st_d                                        # same freshness of every level after every call
-    assert ex_g < ex_d                                         # replayed calls issue their exchanges from the graph
+    if workload == "heat3d":
+        # three large launches per call: recording would only cost the exchange its stream priority -- runs direct
+        assert none == 0 and n_graphs == 0 and ex_g == ex_d
+    else:
+        assert none == 0 and n_graphs >= 1, "sharded calls were not recorded"
+        assert ex_g < ex_d                                     # replayed calls issue their exchanges from the graph
 
 
 def test_fused_jacobi_pairs_on_a_slab_cover_the_interior_and_leave_bands_to_single_sweeps(monkeypatch, tmp_path):

@@ -183,7 +183,16 @@ struct Nccl {
 // (XGB_STAGED_COPY=1) until it has been timed against the driver's pageable path.
 namespace {
 constexpr int kStageLanesMax = 16;
-constexpr size_t kStageChunk = size_t(4) << 20;
+// bytes per staging chunk: XGB_STAGE_CHUNK_MB, default 4
+size_t stage_chunk() {
+    static size_t n = [] {
+        const char *e = getenv("XGB_STAGE_CHUNK_MB");
+        long v = e ? atol(e) : 4;
+        return size_t(v < 1 ? 1 : (v > 64 ? 64 : v)) << 20;
+    }();
+    return n;
+}
+#define kStageChunk (stage_chunk())
 // lanes in use: XGB_STAGE_LANES, default 8 (host memcpy of one thread is ~10 GB/s; PCIe 5 x16 moves ~50)
 int stage_lanes() {
     static int n = [] {

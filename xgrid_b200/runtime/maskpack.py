@@ -28,7 +28,8 @@ def pack(boundary: np.ndarray, n_padded: int):
     shim.check(shim.lib().xgb_mask_pack(flat.ctypes.data_as(C.POINTER(C.c_int32)), n, n_padded,
                                         packed.ctypes.data_as(C.POINTER(C.c_uint8)),
                                         flags.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                        hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(bad), 0))
+                                        hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(bad),
+                                        shim.host_threads(16)))
     return packed, flags, hist.astype(np.int64), bool(bad.value)
 
 

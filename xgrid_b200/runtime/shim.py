@@ -93,6 +93,19 @@ _RESTYPE = {"xgb_last_error": c_char_p}
 _lib = None
 
 
+def host_threads(cap: int) -> int:
+    """Host threads this process should use for copies / mask packing: the cores it may run on, shared with the
+    other ranks of the box (torchrun's LOCAL_WORLD_SIZE), at most `cap`.  Eight ranks that each start eight copy
+    threads and sixteen packing threads on a 32-core host only fight each other (measured: the 8-GPU end-to-end
+    job moved 138 GB at 46 GB/s aggregate)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(2, min(cap, cores // ranks))
+
+
 def lib():
     """The loaded shim; raises if it has not been built (no fallback)."""
     global _lib
@@ -100,6 +113,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise Exception(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(the B200 backend has no CPU fallback)")
+        os.environ.setdefault("XGB_STAGE_LANES", str(host_threads(8)))      # read by the runtime on its first staged copy
         handle = C.CDLL(LIB_PATH)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
