@@ -759,7 +759,9 @@ int xgb_graph_end(xgb_handle stream, xgb_handle *graph_exec, int *kernel_nodes) 
         }
     }
     cudaGraphExec_t exec = nullptr;
-    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    // per-node priorities: a halo exchange captured from the high-priority communication stream must still overtake
+    // the interior sweep it overlaps with when the recorded call is replayed
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, cudaGraphInstantiateFlagUseNodePriority);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess)
         return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
