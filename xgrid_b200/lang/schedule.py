@@ -424,7 +424,10 @@ class _Interpreter:
 # --------------------------------------------------------------------------- deferred calls (temporal blocking)
 _PENDING = None          # {"program", "args", "grid", "key", "count"}: identical calls not yet executed
 PENDING_LIMIT = 4096
-SHARDED_GRAPH_MIN_LAUNCHES = int(os.environ.get("XGB_SHARDED_GRAPH_MIN", "16"))   # slab calls with fewer launches run direct
+# Slab calls are recorded like any other.  The graph is instantiated with per-node priorities (xgb_graph_end), so a
+# recorded halo exchange still overtakes the interior sweep it overlaps with: 8 GPUs, 256x2048^2 slabs, 3.14 ms / step
+# recorded, 3.15 ms direct -- and 3.49 ms when the graph ran every node at the launch stream's priority.
+SHARDED_GRAPH_MIN_LAUNCHES = int(os.environ.get("XGB_SHARDED_GRAPH_MIN", "0"))
 MULTISTEP_MIN_POINTS = int(os.environ.get("XGB_MS_MIN", "16384"))
 MULTISTEP_TAIL = os.environ.get("XGB_MS_TAIL", "1") != "0"     # remainders of a run: tail variant, not single steps
 TILED2_ENABLED = os.environ.get("XGB_TILED2", "1") != "0"
@@ -863,10 +866,7 @@ class Program:
         key = self._graph_key(env, grids) if (self.config.graphs and self.replayable()
                                               and (self.groups or self.callees)) else None
         if sharded and key is not None and self._launches_per_call < SHARDED_GRAPH_MIN_LAUNCHES:
-            # a call of a few large sweeps gains nothing from replay, and a recorded halo exchange loses its
-            # stream priority inside the graph: its NCCL kernels queue behind the interior sweep's CTAs instead of
-            # overtaking them (8 GPUs, 256x2048^2 slabs: 3.49 ms / step recorded vs 3.27 ms direct)
-            key = None
+            key = None                      # (diagnostic knob, off by default: XGB_SHARDED_GRAPH_MIN)
         hit = self._graphs.get(key) if key is not None else None
         if hit is not None:
             # steady state: replay the recorded launches (on slabs: halo exchanges included), then apply the
