@@ -27,7 +27,8 @@ step-at-a-time sweeps read.  Arithmetic per point is the same ex
 as the step-at-a-time kernels: results are bit-identical (tests/test_jacobi2_gpu.py).
 
 Eligibility is decided in three places: statically on the statements (`match`), per launch on
-the grid (shape, not sharded), and once per boundary-mask version on the host (`chains_fit`:
+the grid (shape; on a slab the fused pass covers the interior rows and the rows next to a cut run on row bands,
+lang/launch.py::run_pair), and once per boundary-mask version on the host (`chains_fit`:
 every copy chain must stay within one row and one column of its start and must end at a point
 that no boundary statement writes -- then the statements' program order cannot matter).
 """
