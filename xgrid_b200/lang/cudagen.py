@@ -1185,8 +1185,11 @@ def _emit_multistep(g: Group, module: ModuleBuilder, c: dict, tail: bool = False
     L.append("    for (int q = threadIdx.x * V; q < L; q += NT * V) {")
     L.append("        E a[V], b[V];")
     L.append("        const int64_t gi = g0 + q;                 // stay inside the level's zero slack")
-    L.append("        if (gi >= -64 && gi + V <= p.n0 + 64) { xgb::ld_vec<E, V>(now + gi, a); xgb::ld_vec<E, V>(prev + gi, b); }")
-    L.append("        else { for (int v = 0; v < V; ++v) { a[v] = E(0); b[v] = E(0); } }")
+    L.append("        // p.count != 0: every mask value present has a statement, so each point is rewritten every step and the")
+    L.append("        // previous level is never observed (points outside the grid are zero in both levels): it is not loaded")
+    L.append("        for (int v = 0; v < V; ++v) b[v] = E(0);")
+    L.append("        if (gi >= -64 && gi + V <= p.n0 + 64) { xgb::ld_vec<E, V>(now + gi, a); if (p.count == 0) xgb::ld_vec<E, V>(prev + gi, b); }")
+    L.append("        else { for (int v = 0; v < V; ++v) a[v] = E(0); }")
     L.append("        xgb::st_vec<E, V>(b0 + XSW(q), a); xgb::st_vec<E, V>(b1 + XSW(q), b);")
     L.append("    }")
     L.append("    // A window that lies inside the grid and whose chunk flags are all clear has no boundary point: it")

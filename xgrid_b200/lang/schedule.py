@@ -1048,6 +1048,13 @@ class Program:
                 if grid.sharded:
                     topo = dist.topology()
                     P.open_lo, P.open_hi = int(topo.lo_rank >= 0), int(topo.hi_rank >= 0)
+                else:
+                    # the level two steps back is only ever observed through points no statement writes
+                    # (SURVEY.md F5); when every mask value present has a statement the kernel does not load it
+                    # (a quarter of a launch's HBM traffic).  Slabs keep loading it: a neighbour may own such points.
+                    handled = {a.sweep.mask for a in g.stmts}
+                    present = {k for k in range(255) if grid._mask_count(k) > 0}
+                    P.count = int(present <= handled)
                 if ckey is not None:
                     if len(self._batch_params) > 64:
                         self._batch_params.clear()
