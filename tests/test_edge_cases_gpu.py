@@ -173,6 +173,63 @@ def test_mask_change_between_calls(x64):
         same(g, h)
 
 
+def test_writes_through_arrays_kept_across_calls(x64):
+    """`b = g.boundary` / `a = g.now` kept by the program and written BETWEEN kernel calls (plain attributes in the
+    reference, xgrid/xgrid/__init__.py:38-41,70-72): the next call must see the writes; a deferred 1-D run queued
+    before a mask write still runs with the mask it was called with."""
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def relax(u: f2) -> None:
+        u[0, 0] = 0.25 * (u[0, 1] + u[0, -1] + u[1, 0] + u[-1, 0])
+        with xgrid.boundary(1):
+            u[0, 0] = 1.0
+
+    g, h = pair((40, 48), 9)
+    ref = Interp(relax)
+    b, hb = g.boundary, h.boundary            # kept across the calls
+    relax(g)
+    ref(h)
+    a = g.now                                 # kept: mirrors ring level 0 now, level 1 after the next call
+    ha = h.now
+    for step in range(5):
+        if step == 1:
+            b[3, :] = 1                       # through the kept arrays, never touching g.boundary again
+            hb[3, :] = 1
+        if step == 2:
+            b += 0                            # in-place operator without a change
+            np.copyto(b, np.where(hb == 1, 1, 0).astype(np.int32))
+        if step == 3:
+            a[5:9, 5:9] = 7.0                 # the kept .now array: in the reference it IS a ring level
+            ha[5:9, 5:9] = 7.0
+        relax(g)
+        ref(h)
+        same(g, h)
+    # 1-D deferred run: 12 queued calls see the old mask, the following ones the new mask
+    f1 = xgrid.grid[float, 1]
+
+    @xgrid.kernel()
+    def shift(u: f1, c: float) -> None:
+        u[0] = u[0] - c * (u[0] - u[-1])
+        with xgrid.boundary(1):
+            u[0] = 1.0
+
+    g1, h1 = pair((1 << 15,), 4)
+    ref1 = Interp(shift)
+    b1 = g1.boundary
+    b1[0] = 1
+    h1.boundary[0] = 1
+    for _ in range(12):
+        shift(g1, 0.5)
+        ref1(h1, 0.5)
+    b1[1000] = 1                              # flushes the 12 queued calls first
+    h1.boundary[1000] = 1
+    for _ in range(9):
+        shift(g1, 0.5)
+        ref1(h1, 0.5)
+    same(g1, h1)
+
+
 def test_element_indexing_on_device_level(x64):
     """`u[i]` / `u[i] = v` on a device-resident level move one element and keep the level on
     the device; slices still hand the level to the host."""

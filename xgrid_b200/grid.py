@@ -362,15 +362,15 @@ class Grid:
         rt.sync()
 
     def _adopt_stale_mirror(self, lv: _Level):
-        """A level without a host mirror takes over the STALE mirror of another level of this grid: of a
-        spare level (a buffer that left the ring when a several-steps launch wrote into fresh levels), or of a
-        ring level whose truth is on the device (its host copy would be overwritten by the next download anyway).  Downloading into memory that is already resident -- and possibly
+        """A level without a host mirror takes over the mirror of a SPARE level (a buffer that left the
+        ring when a several-steps launch wrote into fresh levels; its host copy is stale and no public
+        accessor reaches it any more).  Downloading into memory that is already resident -- and possibly
         already page-locked -- avoids first-touch page faults on a fresh array (measured: 28 ms -> pageable
         copy time for a 128 MiB level).  Like the reference's ring, an array handed out by `.now` earlier may
         therefore be written again later."""
-        for donor in [*self._spares, *self._ring]:       # (a ring level whose truth is on the device has a stale mirror too)
-            if donor is lv:
-                continue
+        # (only spares: a RING level keeps its own array, so that an array the program kept from `.now` stays the
+        #  mirror of the level it was handed out for as that level rotates through the ring -- like the reference)
+        for donor in self._spares:
             if donor.host is not None and donor.where == "device" and donor.host.shape == tuple(self.shape):
                 host, donor.host = donor.host, None
                 if donor.pinned:
