@@ -580,3 +580,22 @@ def test_fused_jacobi_pairs_on_a_slab_cover_the_interior_and_leave_bands_to_sing
     k(*gs0, cfg)
     f0 = [r for r in rt0.launches if "jacobi2" in r[0]]
     assert len(f0) == 24 and all((r[3]["r_lo"], r[3]["r_hi"]) == (0, gs0[1].shape[0] - 3) for r in f0)
+
+
+def test_an_assigned_boundary_array_stays_the_mask(rt):
+    """`g.boundary = arr` (plain attribute assignment in the reference): writes through `arr` afterwards reach the next
+    call -- the grid re-compares a program-supplied mask before every call."""
+    k = W.make_kernels()["diffusion_1d"]
+    u = xgrid.Grid((4096,), float)
+    mine = np.zeros(4096, np.int32)
+    mine[0] = 1
+    u.boundary = mine
+    k(u, 0.01, 0.1, 1.0)
+    v1 = u._mask_version
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1
+    mine[-1] = 1                                              # through the program's own array
+    k(u, 0.01, 0.1, 1.0)
+    assert u._mask_version == v1 + 1 and u._mask_snapshot[-1] == 1
+    u.boundary = [0] * 4096                                   # a list is converted: the grid owns the new array
+    assert not u._boundary_foreign

@@ -133,6 +133,7 @@ class Grid:
         self._spares: list[_Level] = []
         self._boundary = np.zeros(self.shape, dtype=np.int32)
         self._boundary_view = None
+        self._boundary_foreign = False  # the mask array was supplied by the program (`g.boundary = arr`)
         self._mask_touched = True
         self._mask_snapshot = None
         self._mask_raw = 0
@@ -193,8 +194,10 @@ class Grid:
         if arr.shape != self.shape:
             self.logger.dead("boundary mask has an incompatible shape")
         self._boundary = np.ascontiguousarray(arr)
-        if self._boundary is value:
-            self._boundary = self._boundary.copy()      # the caller keeps its own array
+        # `g.boundary = my_array`: in the reference my_array IS the mask from then on.  If the assigned array could be
+        # adopted as it is, later writes through `my_array` (which no view can announce) must still be seen: such a
+        # grid re-compares its mask with the snapshot before every call (cost ~ one pass over the mask)
+        self._boundary_foreign = isinstance(value, np.ndarray) and np.shares_memory(self._boundary, value)
         self._mask_touched = True
 
     @property
@@ -445,7 +448,7 @@ class Grid:
         for lv in self._ring:
             if lv.where != "device":
                 self._to_device(lv)
-        if self._mask_touched:
+        if self._mask_touched or self._boundary_foreign:
             self._upload_mask(job.result() if job is not None else None)
 
     def _scratch_level(self) -> _Level:
