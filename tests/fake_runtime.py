@@ -197,6 +197,10 @@ class FakeTransport:
             lv.halo_rows = h
             lv.halo_event = self.rt.event_create()
 
+    def all_agree(self, flag):
+        self.log.append(("all_agree", int(bool(flag)), 0, len(self.rt.launches)))
+        return bool(flag)
+
     def fence_compute(self):
         self.log.append(("fence", 0, 0, len(self.rt.launches)))
 

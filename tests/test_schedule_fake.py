@@ -599,3 +599,31 @@ def test_an_assigned_boundary_array_stays_the_mask(rt):
     assert u._mask_version == v1 + 1 and u._mask_snapshot[-1] == 1
     u.boundary = [0] * 4096                                   # a list is converted: the grid owns the new array
     assert not u._boundary_foreign
+
+
+def test_halo_bookkeeping_does_not_depend_on_which_rank_owns_the_boundary_points(monkeypatch, tmp_path):
+    """A boundary statement whose mask value occurs on ONE rank only (the global top row, say) still marks its level
+    written on every rank: otherwise the ranks' views of what is stale -- and the exchanges they issue -- drift apart."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True, graphs=False)
+    f2 = xgrid.grid[float, 2]
+
+    def make():
+        @xgrid.kernel()
+        def prog(u: f2) -> None:
+            u[0, 0] = u[0, 0] + 1.0
+            with xgrid.boundary(2):
+                u[0, 0] = u[1, 0][0]          # only the rank owning the global top row has value-2 points
+            u[0, 0] = 0.5 * (u[1, 0][0] + u[-1, 0][0])      # implicit sweep: reads level 0 across the cuts
+        return prog
+
+    logs = []
+    for rank in (0, 2):
+        rt, tr = fake_runtime.install_sharded(monkeypatch, rank=rank, world=4)
+        prog = make()                         # (function handles belong to a runtime)
+        g = xgrid.Grid((4 * 32, 64), float)
+        if rank == 0:
+            g.boundary[0, :] = 2
+        for _ in range(3):
+            prog(g)
+        logs.append([(e[0], e[2]) for e in tr.log if e[0].startswith("exchange")])
+    assert logs[0] == logs[1] and len(logs[0]) >= 3, logs

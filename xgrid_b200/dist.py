@@ -167,6 +167,19 @@ class NcclTransport:
         for _, lv, _ in items:
             lv.halo_event = done
 
+    def all_agree(self, flag: bool) -> bool:
+        """Logical AND of `flag` over all ranks (host-side; one tiny all-reduce through torch.distributed's default
+        group).  Every decision that changes WHICH exchanges a call issues -- running a solver loop as fused
+        pairs, say -- must be the same on every rank, or the neighbours' sends and receives no longer pair up."""
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=torch.device("cuda", self.rt.device))
+        else:
+            t = torch.tensor([1 if flag else 0], dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
     def fence_compute(self) -> None:
         """Order the compute stream behind everything enqueued on the comm stream so far (device-side
         wait only): called before a buffer a halo exchange may still be reading is recycled."""

@@ -146,7 +146,24 @@ class Launcher:
 
     # ---- two solver iterations per pass (lang/jacobi2.py)
     def pair_ok(self, pair) -> bool:
-        """Dynamic eligibility of the fused sweep-boundary-sweep pass for this call's grids."""
+        """Dynamic eligibility of the fused sweep-boundary-sweep pass for this call's grids (cached per mask
+        version).  On slabs the fused path issues other exchanges than the step-at-a-time path, so the ranks
+        decide TOGETHER: every rank evaluates its local conditions and joins exactly one host all-reduce per
+        (pair, mask version) -- whatever its local answer, so that no rank waits in the collective alone."""
+        lead = self.grids[pair.sweep.lead]
+        key = (id(pair), lead._mask_version)
+        ok = lead._pair_ok.get(key)
+        if ok is None:
+            if len(lead._pair_ok) > 16:
+                lead._pair_ok.clear()
+            ok = self._pair_ok_local(pair)
+            if lead.sharded:
+                from .. import dist
+                ok = dist.transport().all_agree(ok)
+            lead._pair_ok[key] = ok
+        return ok
+
+    def _pair_ok_local(self, pair) -> bool:
         g = pair.sweep
         lead = self.grids[g.lead]
         c = pair.config
@@ -166,13 +183,7 @@ class Launcher:
             return False
         if not lead._mask_any:
             return True
-        key = (id(pair), lead._mask_version)
-        ok = lead._pair_ok.get(key)
-        if ok is None:
-            if len(lead._pair_ok) > 16:
-                lead._pair_ok.clear()
-            ok = lead._pair_ok[key] = jacobi2.chains_fit(pair, lead._mask_snapshot)
-        return ok
+        return bool(jacobi2.chains_fit(pair, lead._mask_snapshot))
 
     def run_pair(self, pair, env: dict) -> None:
         """Sweep A, boundary statements, sweep B in one pass; then the boundary statements after B.
@@ -310,6 +321,10 @@ class Launcher:
             k = g.stmts[0].sweep.mask
             count = lead._mask_count(k)
             if count == 0:
+                if lead.sharded:
+                    # another rank may own points of this value: the level counts as written HERE too, so that the
+                    # halo bookkeeping -- and with it the sequence of exchanges -- stays the same on every rank
+                    self._mark_written(g)
                 return
             if count * SPARSE_FRACTION <= lead.size:
                 variant = cudagen.VARIANT_SPARSE
