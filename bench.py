@@ -50,7 +50,7 @@ WORKLOADS = {
     "ewmul":     dict(kernel="elementwise_mul", ndim=1, shape=(10000,), stmts=1, bytes_pt=24, steps=2000, warmup=50),
 }
 MAIN = "heat3d"
-SHARDABLE = ("heat3d", "conv1d", "conv1d_nl", "diff1d", "cavity")
+SHARDABLE = ("heat3d", "conv1d", "conv1d_nl", "diff1d", "cavity", "conv2d", "diff2d")
 
 
 def measured_peaks():
@@ -242,6 +242,23 @@ def build_slab_inputs(name: str, shape, rank: int, world: int):
         dt = 1e-4 * (100.0 / (n1 - 1)) ** 2
         z = np.zeros(shape)
         return gshape, [(z, m) for m in W.cavity_masks_slab(n0, n1, lo, hi)], (W.Config(1.0, 0.1, dt, dx, dy),)
+    if name in ("conv2d", "diff2d"):
+        n0, n1 = gshape
+        dx = 2.0 / (n1 - 1)
+        ic = np.ones(shape)
+        a, b = max(n0 // 4, lo), min(n0 // 2, hi)          # the global square hat, local rows
+        if b > a:
+            ic[a - lo:b - lo, n1 // 4:n1 // 2] = 2.0
+        mask = np.zeros(shape, np.int32)
+        mask[:, 0] = 1
+        if rank == 0:
+            mask[0, :] = 1
+        if name == "diff2d":
+            mask[:, -1] = 1
+            if rank == world - 1:
+                mask[-1, :] = 1
+            return gshape, [(ic, mask)], (0.2,)
+        return gshape, [(ic, mask)], (1.0, 0.5 * dx, dx, dx)
     raise SystemExit("multi-GPU bench is defined for the slab-sharded workloads: " + ", ".join(SHARDABLE))
 
 
@@ -618,6 +635,24 @@ def parity_cases(arm: Arm) -> dict:
           [(gg.now, hh.now[s]) for gg, hh in zip(gs, hs)] + [(gg._data[1], hh._data[1][s]) for gg, hh in zip(gs, hs)]
           + [(fused, 72)])
     del gs, hs
+    # 2-D diffusion, 9 deferred calls: four two-step passes + one single step; on slabs the rows next to a cut run
+    # step-at-a-time on row bands beside the two-step pass of the interior (lang/schedule.py::_run_batch2)
+    n0t, n1t = 80 * world + 1, 512
+    ict, mt = np.random.default_rng(21).random((n0t, n1t)), W.shell_mask((n0t, n1t))
+    ut, ht = xgrid.Grid((n0t, n1t), float), oracle.HostGrid((n0t, n1t))
+    s = slab(ut)
+    ut.now[...] = ict[s]
+    ut.boundary[...] = mt[s]
+    ht.now[...] = ict
+    ht.boundary[...] = mt
+    two_before = STATS.get("tiled2", 0)
+    for _ in range(9):
+        k["diffusion_2d"](ut, 0.2)
+        oracle.step_diff2d(ht, 0.2)
+    pairs_t = [(ut.now, ht.now[s]), (ut._data[1], ht._data[1][s])]
+    two = STATS.get("tiled2", 0) - two_before
+    check(f"diff2d {n0t}x{n1t} x9 ({two} two-step passes)", pairs_t + [(two, 4)])
+    del ut, ht
     # overstep modes on slabs: "wrap" turns the ranks into a ring, "limit" clamps at the global ends only;
     # goldens produced by the unmodified reference (tests/golden/make_golden.py; square 32x32)
     from examples import workloads as W2
@@ -783,6 +818,23 @@ def run_ours(args, rank: int, world: int):
             del cgrids
         except Exception as e:                     # a sub-record must never take the main line down
             extra = {"cavity_8192_sharded": {"error": f"{type(e).__name__}: {e}"[:300]}}
+    if world > 1 and select != "none":
+        # config[2] weak-scaled: 16384^2 per GPU, two time steps per pass on the slab interiors
+        extra = extra or {}
+        for wl in ("diff2d", "conv2d"):
+            key = f"{wl}_two_steps_per_pass_sharded"
+            try:
+                arm.rt.trim_pool()
+                wk = arm.configure()[WORKLOADS[wl]["kernel"]]
+                wshape = WORKLOADS[wl]["shape"]
+                wg, win, wsc = build_slab_inputs(wl, wshape, rank, world)
+                wgrids = arm.grids_for(wg, wshape, win)
+                del win
+                wms, wlaunch, wclk, wwarm = device_leg(arm, wk, wgrids, wsc, 50, 6)
+                extra[key] = record_of(arm, wl, wshape, 50, wms, wlaunch, wclk, wwarm)
+                del wgrids
+            except Exception as e:
+                extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         return None
     line = {"metric": "stencil Gpoint-updates/s", "value": rec["value"], "unit": "Gpoint-updates/s",

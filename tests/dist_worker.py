@@ -226,6 +226,54 @@ def main():
         ok = ok and STATS.get("jacobi2", 0) - fused0 == 5 * 24
         for gg, hh in zip(gs, hs):
             ok = ok and np.array_equal(gg.now, hh.now[loc:hic]) and np.array_equal(gg._data[1], hh._data[1][loc:hic])
+        # two steps per pass on slabs (deferred runs of a 2-D kernel): interior rows in the two-step kernel, the rows
+        # next to a cut step-at-a-time on row bands; uneven slabs (one rank owns one row more)
+        n0t, n1t = 80 * world + 1, 512
+        t2_0 = STATS.get("tiled2", 0)
+        for name, stepf, sargs in (("diffusion_2d", oracle.step_diff2d, (0.2,)),
+                                   ("convection_2d", oracle.step_conv2d, (1.0, 0.002, 0.01, 0.01))):
+            ict = np.random.default_rng(21).random((n0t, n1t))
+            mt = np.zeros((n0t, n1t), np.int32)
+            mt[0, :] = mt[-1, :] = mt[:, 0] = mt[:, -1] = 1
+            ut, ht = xgrid.Grid((n0t, n1t), float), HostGrid((n0t, n1t))
+            lot, hit = ut.row_range
+            ut.now[...] = ict[lot:hit]
+            ut.boundary[...] = mt[lot:hit]
+            ht.now[...] = ict
+            ht.boundary[...] = mt
+            for _ in range(9):
+                k[name](ut, *sargs)
+                stepf(ht, *sargs)
+            ok = ok and np.array_equal(ut.now, ht.now[lot:hit]) and np.array_equal(ut._data[1], ht._data[1][lot:hit])
+        ok = ok and STATS.get("tiled2", 0) - t2_0 == 2 * 4
+        # diagonal taps and no boundary statements: at the first / last column a tap leaves its row and -- taps being
+        # linear addresses -- reads the row one further out, which the halo exchange carries as an overhang; with and
+        # without the several-steps kernels
+        f2 = xgrid.grid[float, 2]
+        for temporal in (True, False):
+            xgrid.init(precision="double", distributed=True, device=local, temporal=temporal,
+                       cacheroot=os.environ.get("XG_CACHE", ".xgrid"))
+
+            @xgrid.kernel()
+            def nine_point(u: f2, c: float) -> None:
+                u[0, 0] = c * (u[-1, -1][1] + u[-1, 1][1] + u[1, -1][1] + u[1, 2][1] + u[0, 0][1])
+
+            n09, n19 = 70 * world + 3, 512
+            ic9 = np.random.default_rng(31).random((n09, n19))
+            u9 = xgrid.Grid((n09, n19), float)
+            lo9, hi9 = u9.row_range
+            u9.now[...] = ic9[lo9:hi9]
+            want9 = [ic9, ic9]
+            pad9 = 2 * n19 + 8
+            at9 = np.arange(n09 * n19) + pad9
+            for _ in range(7):
+                nine_point(u9, 0.2)
+                f9 = np.concatenate([np.zeros(pad9), want9[0].ravel(), np.zeros(pad9)])
+                t9 = lambda d0, dk: f9[at9 + d0 * n19 + dk]                              # noqa: E731
+                new9 = 0.2 * ((((t9(-1, -1) + t9(-1, 1)) + t9(1, -1)) + t9(1, 2)) + t9(0, 0))
+                want9 = [new9.reshape(n09, n19), want9[0]]
+            ok = ok and np.array_equal(u9.now, want9[0][lo9:hi9]) and np.array_equal(u9._data[1], want9[1][lo9:hi9])
+            ok = ok and u9._halo_over == 2
         # overstep modes on slabs: ring ("wrap") / chain with clamping at the global ends ("limit");
         # golden produced by the reference (square 32x32) and a non-square NumPy restatement
         gold_dir = os.path.join(ROOT, "tests", "golden")

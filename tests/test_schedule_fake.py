@@ -627,3 +627,98 @@ def test_halo_bookkeeping_does_not_depend_on_which_rank_owns_the_boundary_points
             prog(g)
         logs.append([(e[0], e[2]) for e in tr.log if e[0].startswith("exchange")])
     assert logs[0] == logs[1] and len(logs[0]) >= 3, logs
+
+
+def test_diagonal_taps_make_the_halo_exchange_carry_an_overhang(monkeypatch, tmp_path):
+    """Taps are linear addresses (F10): (-1, -1) at column 0 of a slab's first row reads the LAST element of the row
+    two further down, which whole-row ghosts of depth 1 do not hold.  The grid learns the overhang from the first
+    sweep that needs it, levels exchanged without it count as stale, and the edge-first launches grow by one row
+    (the exchange that follows them sends the head of the first interior row too)."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def nine(u: f2, c: float) -> None:
+        u[0, 0] = c * (u[-1, -1][1] + u[-1, 1][1] + u[1, -1][1] + u[1, 2][1] + u[0, 0][1])
+
+    u = xgrid.Grid((4 * 64, 1024), float)
+    u.now[...] = 1.0
+    nine(u, 0.2)
+    xgrid.flush()                                       # (a lone deferred call runs as an ordinary step)
+    assert u._halo_over == 2                            # (1, 2) leaves its row by two elements
+    bands = [(r[3]["r_lo"], r[3]["r_hi"]) for r in rt.launches]
+    assert bands == [(0, 2), (62, 64), (2, 62)], bands
+    assert ((0, 2)) in u._halo_state()                  # part of the key of a recorded call
+    # a level that was exchanged before the grid learnt about the overhang is refreshed again
+    v = xgrid.Grid((4 * 64, 1024), float)
+    v.now[...] = 1.0
+    lv = v._ring[0]
+    v._prepare_device(1)
+    lv.halo_rows = 1
+    v._need_halo_over(1)
+    assert lv.halo_rows == 0 and v._halo_over == 1
+    v._need_halo_over(1)
+    with pytest.raises(Exception, match="past the ghost rows"):
+        v._need_halo_over(1 << 20)
+
+
+def test_overhang_of_a_slot_counts_only_the_deepest_rows_and_matching_directions():
+    from xgrid_b200.lang.cudagen import Slot
+    s = Slot(0, "u", 1, None, read=True, halo0=1, taps={(-1, 0), (0, -1), (1, 0), (0, 1)})
+    assert s.overhang((64, 128)) == 0                   # axis-aligned star: whole rows suffice
+    s.taps |= {(-1, -1)}
+    assert s.overhang((64, 128)) == 1
+    s.taps |= {(1, -3)}                                 # moves back INTO the ghost row: no overhang
+    assert s.overhang((64, 128)) == 1
+    s3 = Slot(0, "u", 1, None, read=True, halo0=2, taps={(-2, -1, 0), (-1, -2, -2), (2, 1, 1)})
+    assert s3.overhang((16, 32, 100)) == 101            # |dj * n2 + dk| of the taps at depth 2
+    assert Slot(0, "u", 1, None, read=True, halo0=1, taps={(-1,)}).overhang((4096,)) == 0
+
+
+def test_two_step_passes_on_a_slab_cover_the_interior_and_leave_bands_to_single_sweeps(monkeypatch, tmp_path):
+    """Middle rank of 4, 2-D diffusion (taps one row up and down): per pass the two-step kernel covers the rows whose
+    two-step cone stays inside the slab, [3, n0 - 3); next to each cut step 1 runs on row bands into the spare buffer
+    (two rows deeper), the spare's halo is exchanged, and step 2 runs on [0, 3) and [n0 - 3, n0) into the output
+    buffer -- all on the side stream, joined before the next pass."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    k = W.make_kernels()["diffusion_2d"]
+    u = xgrid.Grid((4 * 128, 2048), float)
+    u.now[...] = 1.0
+    u.boundary[:, 0] = u.boundary[:, -1] = 1
+    for _ in range(4):
+        k(u, 0.2)
+    assert rt.launches == []
+    xgrid.flush()
+    n0 = u.shape[0]
+    fused = [r for r in rt.launches if r[0].endswith("tiled2_v2")]
+    assert len(fused) == 2 and rt.launches[-1] is fused[1] and all((r[3]["r_lo"], r[3]["r_hi"]) == (3, n0 - 3) for r in fused)
+    assert [r[3]["opt0"] for r in fused] == [0, 1]
+    first = rt.launches.index(fused[0])
+    bands = [(r[3]["r_lo"], r[3]["r_hi"]) for r in rt.launches[:first]]
+    assert bands == [(0, 5), (n0 - 5, n0), (0, 3), (n0 - 3, n0)], bands
+    x0, x1 = fused[0][3]["aux0"], fused[0][3]["aux1"]
+    step1, step2 = rt.launches[0][3], rt.launches[2][3]
+    spare = step1["s0"]
+    assert step1["s1"] == x0 and spare not in (x0, x1)                 # step 1: u^n -> spare
+    assert step2["s1"] == spare and step2["s0"] == x1                  # step 2: spare -> u^{n+2}
+    # halo exchanges of the first pass: u^n before step 1, the spare before step 2 -- one each, depth 1
+    ex = [(e[1], e[2]) for e in tr.log if e[0] == "exchange" and e[3] <= first]
+    assert ex == [(x0, 1), (spare, 1)], tr.log
+    # the agreement on "every mask value present has a statement" is one collective per flush
+    assert [e for e in tr.log if e[0] == "all_agree"] == [("all_agree", 1, 0, 0)]
+    # second pass: roles of the two ring buffers swapped, same spare; the last pass stores the middle level there
+    assert fused[1][3]["aux0"] == x1 and fused[1][3]["aux1"] == x0 and fused[1][3]["aux2"] == spare
+    assert [lv.dev for lv in u._ring] == [x0, spare]
+    # rank 0 of the chain has no lower neighbour: its pass starts at row 0 and only the upper cut has bands
+    rt0, tr0 = fake_runtime.install_sharded(monkeypatch, rank=0, world=4)
+    k = W.make_kernels()["diffusion_2d"]
+    v = xgrid.Grid((4 * 128, 2048), float)
+    v.boundary[:, 0] = v.boundary[:, -1] = 1
+    for _ in range(2):
+        k(v, 0.2)
+    xgrid.flush()
+    f0 = [r for r in rt0.launches if r[0].endswith("tiled2_v2")]
+    assert [(r[3]["r_lo"], r[3]["r_hi"]) for r in f0] == [(0, v.shape[0] - 3)]
+    assert [(r[3]["r_lo"], r[3]["r_hi"]) for r in rt0.launches[:2]] == [(v.shape[0] - 5, v.shape[0]), (v.shape[0] - 3, v.shape[0])]

@@ -206,19 +206,21 @@ class NcclTransport:
         self.shim.check(self.shim.lib().xgb_halo_exchange(self.shim.C.byref(d), 1, stream))
 
     def exchange(self, items: list, stream: int = 0) -> None:
-        """items: [(grid, level, h)] -- refresh h ghost rows on both sides of each level."""
+        """items: [(grid, level, h)] -- refresh h ghost rows on both sides of each level, plus the grid's overhang
+        (``Grid._need_halo_over``): the few elements of the row one further out that diagonal taps reach."""
         if not items:
             return
         descs = (self.shim.HaloDesc * len(items))()
         for d, (grid, lv, h) in zip(descs, items):
             row = grid.stride0 * grid.itemsize
+            over = getattr(grid, "_halo_over", 0) * grid.itemsize
             n0 = grid.shape[0]
-            d.bytes = h * row
+            d.bytes = h * row + over
             d.lo_rank, d.hi_rank = self.topo.lo_rank, self.topo.hi_rank
-            d.send_lo = lv.dev                     # my first h rows -> rank-1's upper ghost
-            d.recv_lo = lv.dev - h * row           # my lower ghost   <- rank-1's last h rows
-            d.send_hi = lv.dev + (n0 - h) * row    # my last h rows   -> rank+1's lower ghost
-            d.recv_hi = lv.dev + n0 * row          # my upper ghost   <- rank+1's first h rows
+            d.send_lo = lv.dev                            # my first h rows (+) -> rank-1's upper ghost
+            d.recv_lo = lv.dev - h * row - over           # my lower ghost      <- rank-1's last h rows (+)
+            d.send_hi = lv.dev + (n0 - h) * row - over    # my last h rows (+)  -> rank+1's lower ghost
+            d.recv_hi = lv.dev + n0 * row                 # my upper ghost      <- rank+1's first h rows (+)
         self.shim.check(self.shim.lib().xgb_halo_exchange(descs, len(items), stream))
         for _, lv, h in items:
             lv.halo_rows = h

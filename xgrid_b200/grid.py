@@ -145,6 +145,7 @@ class Grid:
         self._pair_ok: dict = {}        # (pair id, mask version) -> fused-pair eligibility (lang/jacobi2.py)
         self._mask_hist = None
         self._ghost = 1                 # zero rows on both sides of axis 0
+        self._halo_over = 0             # slabs: elements beyond whole ghost rows that every exchange also carries
         Grid._instances += 1
         self._serial = Grid._instances  # part of every recorded CUDA graph's key: device addresses can repeat
         self._allocs: list[int] = []    # raw device allocations to free
@@ -480,10 +481,24 @@ class Grid:
     def _halo_state(self) -> tuple:
         """((device pointer, fresh ghost rows) of every ring level and the scratch level): slab grids only."""
         levels = [*self._ring, *([self._scratch] if self._scratch is not None else [])]
-        return tuple((lv.dev, lv.halo_rows) for lv in levels)
+        return tuple((lv.dev, lv.halo_rows) for lv in levels) + ((0, self._halo_over),) * bool(self._halo_over)
+
+    def _need_halo_over(self, elements: int) -> None:
+        """A sweep reads `elements` linear positions past its deepest ghost row (diagonal taps at the first / last
+        column): from now on every halo exchange of this grid carries that many elements more, into the padding
+        next to the ghost rows.  Levels exchanged before count as stale."""
+        if elements <= self._halo_over:
+            return
+        room = SLACK + (2 * self.shape[-1] + 2048 if self.dimension > 1 else 0)
+        if elements > room:
+            raise Exception(f"a stencil tap reaches {elements} elements past the ghost rows of a slab; the layout "
+                            f"has room for {room}")
+        self._halo_over = elements
+        for lv in [*self._ring, *([self._scratch] if self._scratch is not None else [])]:
+            lv.halo_rows = 0
 
     def _restore_halo_state(self, state: tuple) -> None:
-        rows = dict(state)
+        rows = dict(state)          # (an entry with key 0 is the overhang, not a level)
         for lv in [*self._ring, *([self._scratch] if self._scratch is not None else [])]:
             lv.halo_rows = rows.get(lv.dev, 0)
             lv.halo_event = 0

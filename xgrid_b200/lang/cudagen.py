@@ -54,6 +54,24 @@ class Slot:
     read: bool = False
     written: bool = False
     halo0: int = 0          # max |axis-0 offset| this slot is read at (rows a slab must import)
+    taps: set = field(default_factory=set)      # every space offset this slot is read at
+
+    def overhang(self, shape: tuple) -> int:
+        """Elements BEYOND `halo0` whole rows that a slab must import: a tap at the deepest axis-0 offset that also
+        moves along the trailing axes in the same direction leaves its row at the first / last column and -- taps
+        being linear addresses (F10) -- lands in the tail of the row one further out."""
+        if not self.halo0 or len(shape) < 2:
+            return 0
+        strides = [1]
+        for n in reversed(shape[2:]):
+            strides.insert(0, strides[0] * n)
+        over = 0
+        for off in self.taps:
+            if abs(off[0]) == self.halo0:
+                rest = sum(o * st for o, st in zip(off[1:], strides))
+                if rest * off[0] > 0:
+                    over = max(over, abs(rest))
+        return over
 
     @property
     def field(self) -> str:
@@ -358,6 +376,7 @@ def analyse_group(g: Group, scope: dict) -> None:
             sl = slot(ld.variable.name, ld.level, ld.variable.type.element)
             sl.read = True
             sl.halo0 = max(sl.halo0, abs(ld.space_offset[0]))
+            sl.taps.add(tuple(ld.space_offset))
             g.halo0 = max(g.halo0, abs(ld.space_offset[0]) if g.ndim > 1 else 0)
             g.halo_last = max(g.halo_last, abs(ld.space_offset[-1]))
         for e in ir.walk_expr(a.value):

@@ -361,8 +361,12 @@ class Launcher:
             if gr.sharded and lv is not None and lv.halo_event:
                 self.rt.stream_wait_event(self.stream, lv.halo_event)
                 lv.halo_event = 0
-        edge = max((gr._ghost for gr, _ in written if gr.sharded), default=0)
+        # rows to ship after the edges are written: what this program's sweeps read across a cut (the ghost band may
+        # be wider than that -- widened for another program, or for the several-steps kernels)
+        edge = max((min(gr._ghost, self.program.halo0()) for gr, _ in written if gr.sharded), default=0)
         if bands is not None:
+            if variant not in (cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH):
+                raise Exception(f"internal: row bands need a row-range variant, '{variant}' sweeps the whole grid")
             for lo, hi in bands:
                 launch_rows(lo, hi)
             self._mark_written(g)
@@ -372,8 +376,10 @@ class Launcher:
             # slab edges first, then ship the fresh rows to the neighbours on the comm stream
             # while the interior of the slab is still being swept
             from .. import dist
-            launch_rows(0, edge)
-            launch_rows(shape[0] - edge, shape[0])
+            # (an exchange that also carries the overhang of diagonal taps sends the head of one more row)
+            first = edge + (1 if any(gr._halo_over for gr, _ in written if gr.sharded) else 0)
+            launch_rows(0, first)
+            launch_rows(shape[0] - first, shape[0])
             self._mark_written(g)
             items = []
             for gr, s in written:
@@ -381,7 +387,7 @@ class Launcher:
                     lv = gr._scratch if s.level == "scratch" else gr._ring[s.level]
                     items.append((gr, lv, edge))
             dist.transport().exchange_async(items)
-            launch_rows(edge, shape[0] - edge)
+            launch_rows(first, shape[0] - first)
         else:
             launch_rows(0, shape[0])
             self._mark_written(g)
@@ -406,9 +412,11 @@ class Launcher:
             if s.read and s.halo0 > 0:
                 grid = self.grids[s.grid]
                 lv = grid._scratch_level() if s.level == "scratch" else grid._ring[s.level]
-                if grid.sharded and lv.halo_event:
-                    self.rt.stream_wait_event(self.stream, lv.halo_event)
-                    lv.halo_event = 0
+                if grid.sharded:
+                    grid._need_halo_over(s.overhang(grid.shape))
+                    if lv.halo_event:
+                        self.rt.stream_wait_event(self.stream, lv.halo_event)
+                        lv.halo_event = 0
                 reads.append((grid, lv, s.halo0))
         stale = dist.HaloPlan.stale(reads)
         if stale:

@@ -433,6 +433,11 @@ MULTISTEP_TAIL = os.environ.get("XGB_MS_TAIL", "1") != "0"     # remainders of a
 TILED2_ENABLED = os.environ.get("XGB_TILED2", "1") != "0"
 
 
+def _world() -> int:
+    from .. import dist
+    return dist.topology().world
+
+
 def multistep_launches(count: int, T: int, S: int, tail: bool = True) -> tuple[list, int]:
     """Split a run of `count` identical deferred 1-D calls into multi-step launches: full launches of
     T steps, then ONE tail launch of the largest multiple of S that is left if that is at least 2*S
@@ -561,6 +566,7 @@ class Program:
             self._grid_pos = [n for n, (_, t) in enumerate(self.ir.signature.arguments)
                               if isinstance(t, GridT)][0]
         self._graphs: dict = {}
+        self._halo0 = None
         self._batch_params: dict = {}     # (scalars, grid, mask) -> marshalled parameter struct of a deferred 1-D run
         self._launches_per_call = 0       # launches of the last directly executed call
         self._seen: set = set()
@@ -573,12 +579,16 @@ class Program:
 
     def halo0(self, _seen=None) -> int:
         """Largest axis-0 reach of any sweep this call can launch, callee programs included."""
+        if _seen is None and self._halo0 is not None:
+            return self._halo0
         seen = _seen if _seen is not None else set()
         seen.add(id(self.op))
         h = max([1] + [g.halo0 for g in self.groups])
         for op in self.callees:
             if id(op) not in seen:
                 h = max(h, op._program().halo0(seen))
+        if _seen is None:
+            self._halo0 = h             # (groups and callees are fixed once the program is built)
         return h
 
     def replayable(self, _seen=None) -> bool:
@@ -767,9 +777,15 @@ class Program:
             else:
                 t2 = self.groups[0].tiled2
                 nd = getattr(grid, "dimension", 0)
-                defer = (nd == self.groups[0].ndim and not grid.sharded and TILED2_ENABLED
-                         and grid.shape[-1] >= t2["W"] and grid.shape[-1] % t2["V"] == 0 and grid.shape[0] >= 64
+                # (a slab's own row count may differ by one between ranks: the smallest one decides for all)
+                rows = grid.global_shape[0] // _world() if grid.sharded else grid.shape[0] if nd else 0
+                defer = (nd == self.groups[0].ndim and TILED2_ENABLED
+                         and grid.shape[-1] >= t2["W"] and grid.shape[-1] % t2["V"] == 0 and rows >= 64
                          and (nd == 2 or grid.shape[1] >= t2["TJ"]))
+                if defer and grid.sharded:      # the rows next to a cut run on row bands: needs a row-range kernel
+                    from .launch import full_grid_variant
+                    defer = full_grid_variant(self.groups[0], (rows,) + tuple(grid.shape[1:]))[0] in (
+                        cudagen.VARIANT_TILED, cudagen.VARIANT_MARCH)
             if defer:
                 key = tuple(a for n, a in enumerate(args) if n != self._grid_pos)
                 p = _PENDING
@@ -948,7 +964,12 @@ class Program:
             # every cell must be rewritten each step: all mask values present need a statement
             handled = {a.sweep.mask for a in g.stmts}
             present = {k for k in range(255) if grid._mask_count(k) > 0}
-            if not present <= handled:
+            ok = present <= handled
+            if grid.sharded:
+                from .. import dist
+                ok = dist.transport().all_agree(ok)         # another slab may hold a value this one lacks
+                self._join_halo_events(grids)
+            if not ok:
                 passes = 0
         if passes:
             fn = self.function(cudagen.kernel_name(g, cudagen.VARIANT_TILED2, cfg["V"]), cfg["smem"])
@@ -957,7 +978,24 @@ class Program:
             for a, n in enumerate(grid.shape):
                 setattr(P, f"n{a}", n)
             P.rows, P.cols = grid.size // cols, cols
-            P.r_lo, P.r_hi = 0, n0
+            r_lo, r_hi, deep, edge = 0, n0, [], []
+            if grid.sharded:
+                # slab: the two-step pass covers the rows whose two-step cone stays inside the slab (one row
+                # more than the taps say, because a tap that leaves its row at the first / last column lands in the
+                # neighbouring row, F10); the rows next to a cut run step-at-a-time on row bands with the ordinary
+                # kernels -- step 1 into the spare buffer (deep enough for step 2's taps), its halo exchanged by the
+                # usual planner, step 2 into the output buffer -- on a side stream, beside the pass of the interior
+                topo = dist.topology()
+                lo_band = 2 * -cfg["DMIN"] + 1 if topo.lo_rank >= 0 else 0
+                hi_band = 2 * cfg["DMAX"] + 1 if topo.hi_rank >= 0 else 0
+                r_lo, r_hi = lo_band, n0 - hi_band
+                if lo_band:
+                    deep.append((0, min(n0, lo_band + cfg["DMAX"] + 1)))
+                    edge.append((0, lo_band))
+                if hi_band:
+                    deep.append((max(0, n0 - hi_band + cfg["DMIN"] - 1), n0))
+                    edge.append((n0 - hi_band, n0))
+            P.r_lo, P.r_hi = r_lo, r_hi
             gname = g.slots[0].grid
             setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
             setattr(P, f"f_{gname}", grid._flags_dev if grid._mask_any else None)
@@ -968,8 +1006,8 @@ class Program:
             gx = (cols + cfg["W"] - 1) // cfg["W"]
             gj = 1 if grid.dimension == 2 else (grid.shape[1] + cfg["TJ"] - 1) // cfg["TJ"]
             want = max(1, -(-TUNE["min_ctas"] // (gx * gj)))
-            chunk0 = max(64, -(-n0 // want))
-            chunks = (n0 + chunk0 - 1) // chunk0
+            chunk0 = max(64, -(-(r_hi - r_lo) // want))
+            chunks = (r_hi - r_lo + chunk0 - 1) // chunk0
             P.chunk0 = chunk0
             if grid.dimension == 2:
                 gy = min(chunks, 65535)
@@ -980,13 +1018,30 @@ class Program:
                 x0, x1 = grid._ring[0], grid._ring[1]
                 last = pi == passes - 1
                 P.aux0, P.aux1 = x0.dev, x1.dev
-                if last:
+                if last or deep:
                     d = grid._spare_levels(1)[0]
+                if last:
                     P.aux2, P.opt0 = d.dev, 1
                 else:
                     P.aux2, P.opt0 = None, 0
+                if deep:
+                    side, fork, join = rt.side_stream()
+                    rt.event_record_raw(fork, 0)
+                    rt.stream_wait_event(side, fork)
+                    try:
+                        marshal.stream = side
+                        grid._ring = [d, x0]
+                        marshal(g, env, bands=deep)             # step 1 on the bands: u^n -> spare
+                        grid._ring = [x1, d]
+                        marshal(g, env, bands=edge)             # step 2 on the bands: spare -> u^{n+2}
+                    finally:
+                        marshal.stream = 0
+                        grid._ring = [x0, x1]
+                    rt.event_record_raw(join, side)
                 rt.launch(fn, geometry[0], geometry[1], P, smem=cfg["smem"])
                 STATS["tiled2"] = STATS.get("tiled2", 0) + 1
+                if deep:
+                    rt.stream_wait_event(0, join)               # the bands of the output buffer are complete
                 if last:
                     grid._ring, grid._spares = [x1, d], [x0] + grid._spares[1:]
                 else:
