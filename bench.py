@@ -835,6 +835,9 @@ def run_ours(args, rank: int, world: int):
                 del wgrids
             except Exception as e:
                 extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if world > 1:
+        from xgrid_b200 import dist as xdist
+        xdist.quiesce()                 # no exchange kernel still stores into a neighbour's mailbox
     if rank != 0:
         return None
     line = {"metric": "stencil Gpoint-updates/s", "value": rec["value"], "unit": "Gpoint-updates/s",
@@ -844,6 +847,10 @@ def run_ours(args, rank: int, world: int):
             "gpu_launches": rec["gpu_launches"], "clocks": rec["clocks"]}
     if "timesteps_per_s" in rec:
         line["timesteps_per_s"] = rec["timesteps_per_s"]
+    if world > 1:
+        from xgrid_b200 import dist as xdist
+        line["halo_transport"] = {"PeerTransport": "peer memory, one kernel per exchange (csrc/xgb_peer.cu)",
+                                  "NcclTransport": "ncclSend/ncclRecv"}.get(type(xdist.transport()).__name__, "?")
     line.update(legs)
     if parity is not None:
         line["parity"] = parity

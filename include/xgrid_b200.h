@@ -149,6 +149,23 @@ typedef struct xgb_halo_desc {
 } xgb_halo_desc;
 int xgb_halo_exchange(const xgb_halo_desc *descs, int n, xgb_handle stream);
 
+/* ---- the same exchange over peer memory (NVLink / NVSwitch), one kernel per exchange: csrc/xgb_peer.cu ----
+ * Every rank creates a mailbox in its own HBM (a cuMemCreate allocation exported as a POSIX file descriptor) and
+ * publishes a 64-byte ticket {magic, int32 fd at byte 4, size, pid, device}.  A neighbour receives the descriptor
+ * itself over a Unix socket (SCM_RIGHTS; the host side does that), writes its own copy of the descriptor number into
+ * the ticket and calls xgb_peer_open, which maps the mailbox with access for that one allocation -- no device-wide
+ * peer access.  xgb_peer_exchange pushes the edge rows into the neighbours' mailboxes, signals, waits for theirs and
+ * copies them into the ghost rows -- all inside one kernel on `stream`; the rank fields of the descs are ignored (a
+ * neighbour exists where its mailbox is given).  All exchanges of a process must be issued on ONE stream, in the
+ * same order on every rank. */
+int xgb_peer_create(uint64_t slot_bytes, void *ticket_64B);
+int xgb_peer_open(const void *ticket_64B, void **mailbox);          /* the rank's own ticket maps to its own mailbox */
+int xgb_peer_close(void *mailbox);
+int xgb_peer_destroy(void);
+int xgb_peer_reset(void);       /* zero the exchange counters (every rank, between two barriers: neighbours changed) */
+int xgb_peer_slot_bytes(uint64_t *slot_bytes);
+int xgb_peer_exchange(const xgb_halo_desc *descs, int n, void *lo_mailbox, void *hi_mailbox, xgb_handle stream);
+
 #ifdef __cplusplus
 }
 #endif

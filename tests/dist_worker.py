@@ -298,10 +298,12 @@ def main():
                 ko(un, 0.2)
                 want = open_diffusion_global(want, 0.2, omode)
             ok = ok and np.array_equal(un.now, want[lon:hin])
+        xdist.quiesce()
         t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
-            print("DIST_GPU_OK" if int(t.item()) == 1 else "DIST_GPU_MISMATCH")
+            print(("DIST_GPU_OK" if int(t.item()) == 1 else "DIST_GPU_MISMATCH")
+                  + f" transport={type(xdist.transport()).__name__}")
         dist.barrier()
     dist.destroy_process_group()
 

@@ -197,6 +197,9 @@ class FakeTransport:
             lv.halo_rows = h
             lv.halo_event = self.rt.event_create()
 
+    def reserve(self, nbytes):
+        self.reserved = max(getattr(self, "reserved", 0), nbytes)
+
     def all_agree(self, flag):
         self.log.append(("all_agree", int(bool(flag)), 0, len(self.rt.launches)))
         return bool(flag)

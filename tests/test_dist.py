@@ -39,8 +39,8 @@ def test_topology_ring_for_wrap():
     assert not one.ring and (one.lo_rank, one.hi_rank) == (-1, -1)      # a single rank wraps locally
 
 
-def _run(mode, nproc, tmp_path, port):
-    env = dict(os.environ, XG_CACHE=str(tmp_path / "xg"), OMP_NUM_THREADS="2")
+def _run(mode, nproc, tmp_path, port, **extra_env):
+    env = dict(os.environ, XG_CACHE=str(tmp_path / "xg"), OMP_NUM_THREADS="2", **extra_env)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_worker.py"), mode]
@@ -53,9 +53,12 @@ def test_two_ranks_gloo_cpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_two_ranks_nccl_gpu(tmp_path):
+@pytest.mark.parametrize("halo, transport", [("peer", "PeerTransport"), ("nccl", "NcclTransport")])
+def test_two_ranks_nccl_gpu(tmp_path, halo, transport):
+    """Every sharded case of the worker, bit for bit against the single-domain oracle, once per halo transport:
+    the one-kernel exchange over peer memory (the default) and ncclSend/ncclRecv."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _run("gpu", 2, tmp_path, 29612)
-    assert "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    r = _run("gpu", 2, tmp_path, 29612 if halo == "peer" else 29613, XGB_HALO=halo, XGB_PEER_TIMEOUT_S="30")
+    assert f"DIST_GPU_OK transport={transport}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -8,6 +8,7 @@
 // library loads on a machine without a GPU (symbol / ABI checks) and fails
 // loudly -- never silently -- when a GPU call is made there.
 #include "../../include/xgrid_b200.h"
+#include "xgb_internal.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -104,6 +105,17 @@ int require_init() {
     if (g_device < 0) return fail("xgb_init has not been called");
     return 0;
 }
+
+}  // namespace
+
+namespace xgb_internal {
+int fail(const char *msg) { return ::fail(msg); }
+int require_init() { return ::require_init(); }
+cudaStream_t stream_of(xgb_handle h) { return ::as_stream(h); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace xgb_internal
+
+namespace {
 
 // ---- NVRTC, resolved with dlopen -------------------------------------------
 struct Nvrtc {

@@ -146,6 +146,7 @@ class Grid:
         self._mask_hist = None
         self._ghost = 1                 # zero rows on both sides of axis 0
         self._halo_over = 0             # slabs: elements beyond whole ghost rows that every exchange also carries
+        self._halo_reserved = 0         # slabs: bytes per face the halo transport has been asked to make room for
         Grid._instances += 1
         self._serial = Grid._instances  # part of every recorded CUDA graph's key: device addresses can repeat
         self._allocs: list[int] = []    # raw device allocations to free
@@ -449,6 +450,16 @@ class Grid:
         for lv in self._ring:
             if lv.where != "device":
                 self._to_device(lv)
+        if self.sharded:
+            # the transport may need room for the deepest halo this layout allows (whole ghost rows plus the
+            # overhang the padding can take): asked for HERE, before the call may be recorded into a graph -- and
+            # after the levels have their device buffers, so that the transport's own allocations do not sit
+            # between them
+            need = (self._ghost * self.stride0 + SLACK + (2 * self.shape[-1] + 2048 if self.dimension > 1 else 0)) * self.itemsize
+            if need > self._halo_reserved:
+                from . import dist
+                dist.transport().reserve(need)
+                self._halo_reserved = need
         if self._mask_touched or self._boundary_foreign:
             self._upload_mask(job.result() if job is not None else None)
 

@@ -87,6 +87,13 @@ SIGNATURES = {
     "xgb_nccl_init": [c_void_p, c_int, c_int],
     "xgb_nccl_shutdown": [],
     "xgb_halo_exchange": [POINTER(HaloDesc), c_int, Handle],
+    "xgb_peer_create": [c_uint64, c_void_p],
+    "xgb_peer_open": [c_void_p, POINTER(c_void_p)],
+    "xgb_peer_close": [c_void_p],
+    "xgb_peer_destroy": [],
+    "xgb_peer_reset": [],
+    "xgb_peer_slot_bytes": [POINTER(c_uint64)],
+    "xgb_peer_exchange": [POINTER(HaloDesc), c_int, c_void_p, c_void_p, Handle],
 }
 _RESTYPE = {"xgb_last_error": c_char_p}
 
