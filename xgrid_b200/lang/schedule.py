@@ -433,6 +433,25 @@ MULTISTEP_TAIL = os.environ.get("XGB_MS_TAIL", "1") != "0"     # remainders of a
 TILED2_ENABLED = os.environ.get("XGB_TILED2", "1") != "0"
 
 
+def two_step_slab_rows(n0: int, dmin: int, dmax: int, has_lo: bool, has_hi: bool) -> tuple:
+    """Row ranges of a two-steps-per-pass sweep over a slab of `n0` rows whose taps reach axis-0 offsets
+    dmin <= 0 <= dmax: (r_lo, r_hi, deep, edge).  Output rows [r_lo, r_hi) need nothing from a neighbour -- their
+    two-step cone, widened by one row because a tap that leaves its row at the first / last column lands in the
+    adjacent row (F10), stays inside the slab.  The others run step-at-a-time: step 1 on the `deep` ranges (far enough
+    into the slab for step 2's taps, again plus the one row), step 2 on the `edge` ranges.  Checked against a
+    whole-domain NumPy model in tests/test_slab_two_step_model.py."""
+    lo_band = 2 * -dmin + 1 if has_lo else 0
+    hi_band = 2 * dmax + 1 if has_hi else 0
+    deep, edge = [], []
+    if lo_band:
+        deep.append((0, min(n0, lo_band + dmax + 1)))
+        edge.append((0, lo_band))
+    if hi_band:
+        deep.append((max(0, n0 - hi_band + dmin - 1), n0))
+        edge.append((n0 - hi_band, n0))
+    return lo_band, n0 - hi_band, deep, edge
+
+
 def _world() -> int:
     from .. import dist
     return dist.topology().world
@@ -986,15 +1005,8 @@ class Program:
                 # kernels -- step 1 into the spare buffer (deep enough for step 2's taps), its halo exchanged by the
                 # usual planner, step 2 into the output buffer -- on a side stream, beside the pass of the interior
                 topo = dist.topology()
-                lo_band = 2 * -cfg["DMIN"] + 1 if topo.lo_rank >= 0 else 0
-                hi_band = 2 * cfg["DMAX"] + 1 if topo.hi_rank >= 0 else 0
-                r_lo, r_hi = lo_band, n0 - hi_band
-                if lo_band:
-                    deep.append((0, min(n0, lo_band + cfg["DMAX"] + 1)))
-                    edge.append((0, lo_band))
-                if hi_band:
-                    deep.append((max(0, n0 - hi_band + cfg["DMIN"] - 1), n0))
-                    edge.append((n0 - hi_band, n0))
+                r_lo, r_hi, deep, edge = two_step_slab_rows(n0, cfg["DMIN"], cfg["DMAX"], topo.lo_rank >= 0,
+                                                            topo.hi_rank >= 0)
             P.r_lo, P.r_hi = r_lo, r_hi
             gname = g.slots[0].grid
             setattr(P, f"m_{gname}", grid._mask_dev if grid._mask_any else None)
