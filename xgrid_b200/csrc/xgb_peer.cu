@@ -192,10 +192,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS_PER_SM) xgb_peer_exchange_ke
 }
 
 // ---- mailbox memory: CUDA virtual memory management, shared as a POSIX file descriptor ---------------------------------
-// NOT cudaIpcGetMemHandle / cudaIpcOpenMemHandle: opening a legacy IPC handle enables device-wide peer access, and with
-// that enabled the HBM-bound 3-D sweep itself ran 2-4 % slower on B200 -- whether or not a single byte was exchanged
-// (profiles/r2_experiments.md, "peer mailbox").  A cuMemCreate allocation is mapped into the neighbour with access
-// granted for that one allocation only, which is what NCCL does for its own peer buffers.
+// NOT cudaIpcGetMemHandle / cudaIpcOpenMemHandle: opening a legacy IPC handle enables device-wide peer access.  A
+// cuMemCreate allocation is mapped into the neighbour with access granted for that one allocation only, which is what
+// NCCL does for its own peer buffers.  (Measured on 2 x B200, the HBM-bound 3-D sweep ran ~3 % slower with the mailboxes
+// mapped -- under either scheme, and whether or not a single byte was exchanged through them; not understood yet,
+// profiles/r2_experiments.md "Halo exchange over peer memory".)
 struct Vmm {
     bool ready = false;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;

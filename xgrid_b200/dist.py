@@ -254,7 +254,8 @@ class PeerTransport(_Transport):
     descriptor: every rank serves its descriptor on an abstract Unix socket whose name is gathered once through
     torch.distributed, and a neighbour's mailbox is fetched and mapped on first use, so switching between the open
     chain and the ring (overstep="wrap") needs no new collective.  (Legacy CUDA IPC handles would be simpler, but
-    opening one enables device-wide peer access, which by itself slowed the 3-D sweep by 2-4 %.)"""
+    opening one enables device-wide peer access.  Measured, the 3-D sweep runs ~3 % slower beside EITHER kind of
+    mapping, which is why this transport is opt-in: DESIGN.md section 5.)"""
 
     _generation = 0         # mailboxes created by this process so far (part of the socket name)
 
