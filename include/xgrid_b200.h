@@ -150,6 +150,7 @@ typedef struct xgb_halo_desc {
 int xgb_halo_exchange(const xgb_halo_desc *descs, int n, xgb_handle stream);
 
 /* ---- the same exchange over peer memory (NVLink / NVSwitch), one kernel per exchange: csrc/xgb_peer.cu ----
+ * New work like the block above: the reference is single-address-space OpenMP.
  * Every rank creates a mailbox in its own HBM (a cuMemCreate allocation exported as a POSIX file descriptor) and
  * publishes a 64-byte ticket {magic, int32 fd at byte 4, size, pid, device}.  A neighbour receives the descriptor
  * itself over a Unix socket (SCM_RIGHTS; the host side does that), writes its own copy of the descriptor number into
