@@ -22,6 +22,8 @@ pass synccheck smoke 400 python -c "$SMOKE"
 # tiled2 (two steps per pass), jacobi2 (fused solver pairs), 3-D tiled, short / tail multistep: small parity cases
 pass racecheck pipelines 900 python -m pytest tests/test_sanitize_cases_gpu.py -q -x -m gpu
 pass memcheck pipelines 600 python -m pytest tests/test_sanitize_cases_gpu.py -q -x -m gpu
+# the peer-memory halo exchange kernel as a ring of one rank: all copy widths, split batches, graph replay
+pass memcheck peer_exchange 300 python -m pytest tests/test_peer_gpu.py -q -x -m gpu
 # control: the textbook single-stage bulk-copy + mbarrier pattern (correct by construction).  A report here means
 # racecheck does not model completion through mbarrier::complete_tx
 pass racecheck control 300 python -m pytest tests/test_racecheck_control_gpu.py -q -x -m gpu -k single_stage
