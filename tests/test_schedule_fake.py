@@ -722,3 +722,33 @@ def test_two_step_passes_on_a_slab_cover_the_interior_and_leave_bands_to_single_
     f0 = [r for r in rt0.launches if r[0].endswith("tiled2_v2")]
     assert [(r[3]["r_lo"], r[3]["r_hi"]) for r in f0] == [(0, v.shape[0] - 3)]
     assert [(r[3]["r_lo"], r[3]["r_hi"]) for r in rt0.launches[:2]] == [(v.shape[0] - 5, v.shape[0]), (v.shape[0] - 3, v.shape[0])]
+
+
+def test_a_sweep_with_taps_along_the_rows_only_still_imports_one_ghost_row(monkeypatch, tmp_path):
+    """u[0, -1] at column 0 of a slab's first row is a linear address in the row below -- the neighbour's last row.  A
+    full-grid sweep therefore exchanges one row although no tap has an axis-0 offset; a lone boundary statement (a
+    sparse group, confined by its mask -- the cavity's wall copies) keeps exchanging nothing."""
+    xgrid.init(precision="double", cacheroot=str(tmp_path / "xg"), distributed=True, temporal=False)
+    rt, tr = fake_runtime.install_sharded(monkeypatch, rank=1, world=4)
+    f2 = xgrid.grid[float, 2]
+
+    @xgrid.kernel()
+    def along_rows(u: f2, c: float) -> None:
+        u[0, 0] = c * (u[0, -1][1] + u[0, 2][1])
+
+    @xgrid.kernel()
+    def wall_copy(u: f2, p: f2) -> None:
+        with xgrid.boundary(3):
+            p[0, 0] = u[0, -1]
+
+    u, p = xgrid.Grid((4 * 64, 1024), float), xgrid.Grid((4 * 64, 1024), float)
+    u.now[...] = 1.0
+    along_rows(u, 0.5)
+    src = u._ring[1]
+    assert [(e[1], e[2]) for e in tr.log if e[0] == "exchange"] == [(src.dev, 1)], tr.log
+    n = len(tr.log)
+    w = xgrid.Grid((4 * 64, 1024), float)               # freshly uploaded: its ghost rows are stale
+    w.now[...] = 2.0
+    p.boundary[:, -1] = 3
+    wall_copy(w, p)
+    assert [e for e in tr.log[n:] if e[0].startswith("exchange")] == [], tr.log[n:]

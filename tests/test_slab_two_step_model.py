@@ -13,6 +13,7 @@ STENCILS = {
     "upwind": [(0, 0), (-1, 0), (0, -1)],
     "diagonal": [(-1, -1), (-1, 1), (1, -1), (1, 2), (0, 0)],
     "downwind2": [(0, 0), (2, 0), (1, 1)],
+    "along_rows": [(0, 0), (0, -1), (0, 2)],               # no axis-0 offset at all: the linear wrap still crosses the cut
 }
 
 

@@ -390,6 +390,15 @@ def analyse_group(g: Group, scope: dict) -> None:
                     g.shapes.append(e.variable.name)
     g.lead = g.stmts[0].sweep.grid.name
     g.sparse = all(a.sweep.mask != 0 for a in g.stmts) and len(g.stmts) == 1
+    if g.ndim > 1 and not g.sparse:
+        # a slot read only at axis-0 offset 0 but off its column / plane position -- u[0, -1] -- still leaves its row
+        # at the first / last column (taps are linear addresses, F10) and then reads the adjacent row: on a slab that
+        # is a ghost row, so a sweep over the whole grid imports one.  (A lone boundary statement -- a sparse group --
+        # is confined by its mask; the cavity's wall copies are of that kind and keep exchanging nothing.)
+        for sl in g.slots:
+            if sl.read and sl.halo0 == 0 and any(any(o != 0 for o in off[1:]) for off in sl.taps):
+                sl.halo0 = 1
+                g.halo0 = max(g.halo0, 1)
 
 
 def vector_widths(g: Group) -> tuple:
